@@ -1,0 +1,148 @@
+/*
+ * qwen3tts_b200.h — C ABI of the B200-native Qwen3-TTS hot-path library (libqwen3tts_b200.so).
+ *
+ * The reference (QwenLM/Qwen3-TTS) is pure Python with no FFI/plugin interface, so the
+ * boundary below is defined at the two narrowest seams of the reference and each entry point cites the
+ * reference interface it replaces (paths relative to /root/reference/qwen_tts/):
+ *
+ *   seam B (AR)   : Qwen3TTSTalkerForConditionalGeneration.generate(inputs_embeds, attention_mask,
+ *                   trailing_text_hidden, tts_pad_embed, **talker_kwargs)
+ *                   as called at core/models/modeling_qwen3_tts.py:2272-2278, including the per-frame
+ *                   forward :1636-1744, the nested code-predictor generate :1671-1680 / :1250-1312 and the
+ *                   HF logits processors + sampling configured at :2044-2066.
+ *   seam C (codec): Qwen3TTSTokenizerV2Decoder.forward / chunked_decode
+ *                   core/tokenizer_12hz/modeling_qwen3_tts_tokenizer_v2.py:869-896 (called by
+ *                   Qwen3TTSTokenizerV2Model.decode :993-1024).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; q3_last_error() gives the message
+ *     (thread-local).
+ *   - all `dev` pointers are CUDA device pointers on the engine's device; the caller (PyTorch) OWNS them.
+ *     The engine owns only what it allocates itself (packed weights, KV cache, workspaces).
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream); work is
+ *     enqueued on it, calls do not synchronise unless documented.  One engine = one device, not re-entrant.
+ *   - bf16 tensors are raw uint16 storage (torch.bfloat16).  No torch types cross this boundary.
+ */
+#ifndef QWEN3TTS_B200_H
+#define QWEN3TTS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define Q3_ABI_VERSION 1
+#define Q3_MAX_BATCH 32        /* sequences per engine pass (reference batches = padded batch on one GPU) */
+#define Q3_NUM_GROUPS_MAX 32
+
+typedef struct q3_engine q3_engine; /* AR engine: talker + code predictor + sampler */
+typedef struct q3_codec q3_codec;   /* 12 Hz codec decoder */
+
+/* One decoder stack.  Mirrors Qwen3TTSTalkerConfig / Qwen3TTSTalkerCodePredictorConfig
+ * (core/models/configuration_qwen3_tts.py:370-404, :187-212); values come from the loaded config. */
+typedef struct {
+  int32_t hidden_size, num_layers, num_heads, num_kv_heads, head_dim, intermediate_size, vocab_size;
+  float rms_eps;
+} q3_stack_cfg;
+
+typedef struct {
+  q3_stack_cfg talker, cp;
+  int32_t num_code_groups;   /* 16 */
+  int32_t has_cp_projection; /* small_to_mtp_projection is a Linear (1.7B) or Identity (0.6B), :1171-1174 */
+  int32_t codec_eos_token_id;
+  int32_t max_batch;         /* <= Q3_MAX_BATCH */
+  int32_t max_ctx;           /* talker KV capacity per sequence (prompt + frames) */
+  int32_t device;            /* CUDA ordinal */
+} q3_engine_cfg;
+
+/* Generation kwargs of seam B (modeling_qwen3_tts.py:2044-2066; defaults inference/qwen3_tts_model.py:287-352). */
+typedef struct {
+  int32_t do_sample, top_k;
+  float top_p, temperature, repetition_penalty;
+  int32_t subtalker_dosample, subtalker_top_k;
+  float subtalker_top_p, subtalker_temperature;
+  int32_t min_new_tokens;  /* 2 */
+  int32_t suppress_eos;    /* benchmark-only: fixed horizon (EOS never sampled) */
+  uint64_t seed;           /* Philox key; u = philox(seed; row, frame, group) */
+} q3_sampling;
+
+int q3_abi_version(void);
+const char* q3_last_error(void);
+
+/* ---------------------------------------------------------------- AR engine (seam B) */
+int q3_engine_create(const q3_engine_cfg* cfg, q3_engine** out);
+void q3_engine_destroy(q3_engine* e);
+
+/* Copy+repack one weight from device memory (bf16, row-major [rows][cols], i.e. nn.Linear/nn.Embedding
+ * layout).  `name` is one of the engine tensor names documented in INTEGRATION.md, e.g.
+ *   "talker.layers.<i>.qkv"  = cat(q_proj,k_proj,v_proj).weight          (:740-748)
+ *   "talker.layers.<i>.gate_up" = gate/up rows interleaved in blocks of 8 (:848-849)
+ *   "talker.layers.<i>.o", ".down", ".ln1", ".ln2", ".q_norm", ".k_norm"
+ *   "talker.norm", "talker.codec_head", "talker.codec_embedding", "talker.rope_cos", "talker.rope_sin"
+ *   "cp.layers.<i>.*", "cp.norm", "cp.proj", "cp.proj_bias", "cp.lm_head.<j>", "cp.codec_embedding.<j>",
+ *   "cp.rope_cos", "cp.rope_sin".
+ * The source may be freed after the call returns (the call synchronises the copy stream). */
+int q3_engine_load_tensor(q3_engine* e, const char* name, const void* dev_bf16, int64_t rows, int64_t cols);
+int q3_engine_finalize(q3_engine* e); /* verifies that every tensor is present */
+
+/* Prefill = first `talker.generate` forward (modeling_qwen3_tts.py:1665-1667 -> :1457-1561).
+ * embeds: bf16 [sum(lens)][H], rows of sequence 0 first (NO padding: the reference's left-pad+mask,
+ * :2239-2254, is equivalent to per-sequence positions 0..len-1).  lens: host int32[B].
+ * trailing: bf16 [B][trailing_stride][H] (row b valid for trailing_lens[b] steps, then tts_pad, :1689-1692);
+ * tts_pad: bf16 [H].  Resets all per-request state (per request, never on a module: SURVEY F10) and samples
+ * codebook-0 of frame 0. */
+int q3_prefill(q3_engine* e, int32_t B, const void* embeds_dev, const int32_t* lens_host,
+               const void* trailing_dev, const int32_t* trailing_lens_host, int32_t trailing_stride,
+               const void* tts_pad_dev, const q3_sampling* sp, void* stream);
+
+/* Run up to `max_frames` further frame-steps (code predictor x15 -> embed -> talker -> head -> sample),
+ * stopping early once every row has sampled EOS.  No host sync per token (HF syncs every token).
+ * codes_dev: int32 [B][codes_stride][num_code_groups], frame f of row b at [b][f][:]; frames accumulate
+ * across calls (streaming = repeated calls with small max_frames).  Asynchronous. */
+int q3_decode(q3_engine* e, int32_t max_frames, int32_t* codes_dev, int32_t codes_stride, void* stream);
+
+/* After synchronising `stream`: frames_done = frames whose 16 codes are complete (same for all rows);
+ * n_valid[b] = frames of row b before its first EOS (== modeling_qwen3_tts.py:2283-2290 trim);
+ * finished[b] = 1 once row b sampled EOS.  Host pointers (may be NULL). */
+int q3_get_progress(q3_engine* e, int32_t* frames_done, int32_t* n_valid, int32_t* finished);
+
+/* Test hooks (used by tests/ only): teacher forcing and raw-logit capture.
+ * forced: int32 [B][n_frames][G] device (or NULL to disable); talker_logits: fp32 [n_frames+1][B][V];
+ * cp_logits: fp32 [n_frames][G-1][B][Vc].  Pointers must stay valid until cleared. */
+int q3_set_debug(q3_engine* e, const int32_t* forced_dev, int32_t n_frames, float* talker_logits_dev,
+                 float* cp_logits_dev);
+
+/* Bytes the fused frame-step kernel must stream per step for batch B at mean context S
+ * (W_talker + W_cp_unique + B*(S+1)*KV_tok), and the no-residency figure. */
+int q3_algorithmic_bytes(q3_engine* e, int32_t B, int32_t S, double* a_bytes, double* a_stream_bytes);
+
+/* ---------------------------------------------------------------- codec decoder (seam C) */
+/* Mirrors Qwen3TTSTokenizerV2DecoderConfig (core/tokenizer_12hz/configuration_qwen3_tts_tokenizer_v2.py:72-93). */
+typedef struct {
+  int32_t codebook_size, codebook_dim, hidden_size, latent_dim;
+  int32_t num_heads, num_kv_heads, head_dim, sliding_window, intermediate_size, num_layers, num_quantizers;
+  int32_t n_upsample_rates;    int32_t upsample_rates[8];    /* (8,5,4,3) */
+  int32_t n_upsampling_ratios; int32_t upsampling_ratios[8]; /* (2,2)     */
+  int32_t decoder_dim;
+  float rms_eps, rope_theta;
+  int32_t max_frames;  /* per forward (chunk_size + left_context = 325 in the reference) */
+  int32_t max_batch;
+  int32_t device;
+} q3_codec_cfg;
+
+int q3_codec_create(const q3_codec_cfg* cfg, q3_codec** out);
+void q3_codec_destroy(q3_codec* c);
+/* fp32 source tensors in the reference decoder's own state_dict layout and names
+ * (e.g. "decoder.1.block.2.conv1.conv.weight" [Cout][Cin][k]); the engine converts/re-lays them out. */
+int q3_codec_load_tensor(q3_codec* c, const char* name, const void* dev_f32, const int64_t* shape, int32_t ndim);
+int q3_codec_finalize(q3_codec* c);
+/* One full causal forward == Qwen3TTSTokenizerV2Decoder.forward (…v2.py:869-884).
+ * codes: int32 [B][K][T] device; wav: fp32 [B][T*upsample] device.  Asynchronous. */
+int q3_codec_forward(q3_codec* c, const int32_t* codes_dev, int32_t B, int32_t T, float* wav_dev, void* stream);
+int q3_codec_total_upsample(q3_codec* c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QWEN3TTS_B200_H */
