@@ -133,9 +133,12 @@ typedef struct {
 
 int q3_codec_create(const q3_codec_cfg* cfg, q3_codec** out);
 void q3_codec_destroy(q3_codec* c);
-/* fp32 source tensors in the reference decoder's own state_dict layout and names
- * (e.g. "decoder.1.block.2.conv1.conv.weight" [Cout][Cin][k]); the engine converts/re-lays them out. */
-int q3_codec_load_tensor(q3_codec* c, const char* name, const void* dev_f32, const int64_t* shape, int32_t ndim);
+/* Engine-native tensors, converted from the reference decoder's state_dict by the host
+ * (qwen3-tts_b200/codec.py documents every name; INTEGRATION.md lists the mapping).  GEMM weights are bf16
+ * [N][ntaps*Kp] (K-major per tap, Kp = K rounded up to 64; Conv1d taps in kernel order, ConvTranspose1d as
+ * N = stride*Cout with 2 taps), biases / SnakeBeta / LayerScale / LayerNorm parameters fp32.  dtype is implied
+ * by the name (".w", ".table", ".proj", ".norm", ".ln1", ".ln2", ".cos", ".sin" = bf16; the rest fp32). */
+int q3_codec_load_tensor(q3_codec* c, const char* name, const void* dev, const int64_t* shape, int32_t ndim);
 int q3_codec_finalize(q3_codec* c);
 /* One full causal forward == Qwen3TTSTokenizerV2Decoder.forward (…v2.py:869-884).
  * codes: int32 [B][K][T] device; wav: fp32 [B][T*upsample] device.  Asynchronous. */

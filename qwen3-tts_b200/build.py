@@ -49,7 +49,7 @@ def build(force=False, verbose=False):
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {s}:\n{r.stdout}\n{r.stderr}")
         objs.append(obj)
-    cmd = [_nvcc(), "-shared", "-cudart", "shared", "-o", LIB_PATH] + objs
+    cmd = [_nvcc(), "-shared", "-cudart", "shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -700,7 +700,9 @@ __device__ void sample_phase(const Phase& ph, const KParams& P, unsigned char* s
       for (int i = tid; i < V; i += NTHREADS) { const float p = __expf(sv[i] - mx); pv[i] = p; tot += p; }
       tot = block_sum(tot, red);
       __syncthreads();
-      for (int i = tid; i < V; i += NTHREADS) {
+      unsigned int rm_mask = 0;  // removal flags stay in registers until every thread has finished reading pv/sv
+      int slot = 0;
+      for (int i = tid; i < V; i += NTHREADS, ++slot) {
         const float si = sv[i];
         bool rm = false;
         if (si != -INFINITY) {
@@ -714,11 +716,12 @@ __device__ void sample_phase(const Phase& ph, const KParams& P, unsigned char* s
           }
           rm = (cum / tot <= 1.0f - top_p) && !is_top;
         }
-        pv[i] = rm ? -1.f : 0.f;
+        if (rm) rm_mask |= 1u << slot;
       }
       __syncthreads();
-      for (int i = tid; i < V; i += NTHREADS)
-        if (pv[i] < 0.f) sv[i] = -INFINITY;
+      slot = 0;
+      for (int i = tid; i < V; i += NTHREADS, ++slot)
+        if (rm_mask & (1u << slot)) sv[i] = -INFINITY;
       __syncthreads();
     }
     // softmax + inverse CDF in token-id order (blocked mapping for the scan)

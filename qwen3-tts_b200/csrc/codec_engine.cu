@@ -1,0 +1,486 @@
+// Qwen3-TTS-Tokenizer-12Hz codec DECODER on B200 (sm_100a): codes -> 24 kHz waveform.
+// Replaces Qwen3TTSTokenizerV2Decoder.forward (qwen_tts/core/tokenizer_12hz/modeling_qwen3_tts_tokenizer_v2.py:869-884).
+//
+// Layout: every activation is channels-last bf16 [B][T][C]; every Conv1d / ConvTranspose1d / Linear is ONE
+// tcgen05 tap-GEMM launch (gemm_sm100.cu) whose A tiles are TMA-loaded with a per-tap row shift — no im2col
+// buffer — with bias, LayerScale, residual add and the *next* layer's SnakeBeta fused into the epilogue.
+// Small row-wise ops (RVQ gather, RMSNorm, RoPE, 72-frame sliding-window attention, depthwise conv + LayerNorm,
+// the final 96->1 conv + clamp) are plain CUDA kernels: they are <2 % of the FLOPs and HBM-trivial.
+#include "common.cuh"
+#include "gemm_sm100.cuh"
+#include "../../include/qwen3tts_b200.h"
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct DevTensor {
+  void* p = nullptr;
+  int dtype = 0;  // 0 = bf16, 1 = f32
+  int64_t numel = 0;
+};
+
+// ---------------------------------------------------------------------------------------------- small kernels
+// RVQ decode (…v2.py:815-821, :721-727, :676-679): e[b][t][0:D] = table[0][c0]; e[b][t][D:2D] = sum_{k>=1} table[k][c_k]
+__global__ void rvq_gather_kernel(const int* __restrict__ codes, const bf16* __restrict__ table, bf16* __restrict__ e,
+                                  int B, int K, int T, int D, int bins) {
+  const int bt = blockIdx.x;  // b*T + t
+  const int b = bt / T, t = bt % T;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const int c0 = codes[((size_t)b * K + 0) * T + t];
+    e[(size_t)bt * 2 * D + d] = table[((size_t)0 * bins + c0) * D + d];
+    float acc = 0.f;
+    for (int k = 1; k < K; ++k) {
+      const int c = codes[((size_t)b * K + k) * T + t];
+      const float v = bf2f(table[((size_t)k * bins + c) * D + d]);
+      acc = (k == 1) ? v : rbf(acc + v);  // the reference accumulates in the model dtype
+    }
+    e[(size_t)bt * 2 * D + D + d] = f2bf(acc);
+  }
+}
+
+// RMSNorm over the last dim (…v2.py:383-388): one warp per row
+__global__ void rmsnorm_rows_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y, int rows,
+                                    int C, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const bf16* xr = x + (size_t)row * C;
+  float ss = 0.f;
+  for (int i = lane; i < C; i += 32) { const float v = bf2f(xr[i]); ss += v * v; }
+  ss = warp_sum(ss);
+  const float inv = rsqrtf(ss / (float)C + eps);
+  for (int i = lane; i < C; i += 32) y[(size_t)row * C + i] = f2bf(rbf(bf2f(xr[i]) * inv) * bf2f(w[i]));
+}
+
+// RoPE in place on the q and k parts of qkv [rows][3*nh*hd] (…v2.py:329, apply_rotary_pos_emb); positions = t
+__global__ void rope_qk_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ cosT, const bf16* __restrict__ sinT, int B,
+                               int T, int nh, int hd) {
+  const int half = hd / 2;
+  const size_t total = (size_t)B * T * 2 * nh * half;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int f = (int)(i % half);
+    const int h = (int)((i / half) % (2 * nh));  // q heads then k heads
+    const size_t bt = i / ((size_t)half * 2 * nh);
+    const int t = (int)(bt % T);
+    bf16* v = qkv + bt * (size_t)(3 * nh * hd) + (size_t)h * hd;
+    const float c = bf2f(cosT[(size_t)t * half + f]), s = bf2f(sinT[(size_t)t * half + f]);
+    const float x1 = bf2f(v[f]), x2 = bf2f(v[f + half]);
+    v[f] = f2bf(rbf(x1 * c) + rbf(-x2 * s));
+    v[f + half] = f2bf(rbf(x2 * c) + rbf(x1 * s));
+  }
+}
+
+// causal sliding-window attention, one warp per (b, head, t) (…v2.py:321-354; window: key k visible iff 0 <= t-k < W)
+__global__ void swa_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int B, int T, int nh, int hd,
+                                     int window) {
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= B * T * nh) return;
+  const int lane = threadIdx.x & 31;
+  const int h = wid % nh, t = (wid / nh) % T, b = wid / (nh * T);
+  const int ld = 3 * nh * hd;
+  const bf16* q = qkv + ((size_t)b * T + t) * ld + (size_t)h * hd;
+  const int k0 = max(0, t - window + 1);
+  const int nk = t - k0 + 1;
+  const float scale = rsqrtf((float)hd);
+  // scores: lane handles keys lane, lane+32, lane+64 (window <= 96)
+  float sc[3];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int kk = lane + 32 * r;
+    sc[r] = -INFINITY;
+    if (kk < nk) {
+      const bf16* kp = qkv + ((size_t)b * T + k0 + kk) * ld + (size_t)(nh + h) * hd;
+      float d = 0.f;
+      for (int i = 0; i < hd; i += 2) {
+        const uint32_t qa = *reinterpret_cast<const uint32_t*>(q + i), ka = *reinterpret_cast<const uint32_t*>(kp + i);
+        d += bf16lo(qa) * bf16lo(ka) + bf16hi(qa) * bf16hi(ka);
+      }
+      sc[r] = rbf(rbf(d) * scale);  // bf16 matmul output, then * scaling in bf16 (eager path)
+      mx = fmaxf(mx, sc[r]);
+    }
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) { sc[r] = (sc[r] == -INFINITY) ? 0.f : __expf(sc[r] - mx); sum += sc[r]; }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  // output: lanes over dims (hd <= 64 -> 2 per lane), loop over keys with shuffles
+  float o0 = 0.f, o1 = 0.f;
+  for (int kk = 0; kk < nk; ++kk) {
+    const float p = rbf(__shfl_sync(0xffffffffu, sc[kk >> 5], kk & 31) * inv);  // softmax cast to bf16
+    const bf16* vp = qkv + ((size_t)b * T + k0 + kk) * ld + (size_t)(2 * nh + h) * hd;
+    if (lane * 2 < hd) {
+      const uint32_t va = *reinterpret_cast<const uint32_t*>(vp + lane * 2);
+      o0 += p * bf16lo(va);
+      o1 += p * bf16hi(va);
+    }
+  }
+  if (lane * 2 < hd)
+    *reinterpret_cast<uint32_t*>(out + ((size_t)b * T + t) * (size_t)(nh * hd) + (size_t)h * hd + lane * 2) = pack_bf16(o0, o1);
+}
+
+// ConvNeXt front: depthwise causal conv k=7 + LayerNorm(eps 1e-6) (…v2.py:230-232); one block per (b,t)
+__global__ void dwconv_ln_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                 const float* __restrict__ lnw, const float* __restrict__ lnb, bf16* __restrict__ y, int B, int T,
+                                 int C) {
+  extern __shared__ float sh[];  // [C] conv outputs + 64 scratch
+  const int bt = blockIdx.x;
+  const int t = bt % T;
+  float s1 = 0.f, s2 = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = bias[c];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int tt = t - 6 + j;
+      if (tt >= 0) acc += w[c * 7 + j] * bf2f(x[((size_t)bt - 6 + j) * C + c]);
+    }
+    acc = rbf(acc);
+    sh[c] = acc;
+    s1 += acc;
+    s2 += acc * acc;
+  }
+  float* red = sh + C;
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = s1; red[32 + (threadIdx.x >> 5)] = s2; }
+  __syncthreads();
+  float a = 0.f, q = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[i]; q += red[32 + i]; }
+  const float mean = a / C;
+  const float var = fmaxf(q / C - mean * mean, 0.f);
+  const float inv = rsqrtf(var + 1e-6f);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) y[(size_t)bt * C + c] = f2bf((sh[c] - mean) * inv * lnw[c] + lnb[c]);
+}
+
+// final causal conv k=7, C -> 1, + clamp(-1,1) (…v2.py:863,884); one thread per output sample
+__global__ void final_conv_kernel(const bf16* __restrict__ x, const float* __restrict__ w /*[7][C]*/, float bias,
+                                  float* __restrict__ wav, int B, int T, int C) {
+  const size_t total = (size_t)B * T;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i % T);
+    float acc = bias;
+    for (int j = 0; j < 7; ++j) {
+      const int tt = t - 6 + j;
+      if (tt < 0) continue;
+      const bf16* xr = x + (i - 6 + j) * (size_t)C;
+      for (int c = 0; c < C; c += 8) {
+        const uint4 v = *reinterpret_cast<const uint4*>(xr + c);
+        const float* wr = w + j * C + c;
+        acc += bf16lo(v.x) * wr[0] + bf16hi(v.x) * wr[1] + bf16lo(v.y) * wr[2] + bf16hi(v.y) * wr[3] +
+               bf16lo(v.z) * wr[4] + bf16hi(v.z) * wr[5] + bf16lo(v.w) * wr[6] + bf16hi(v.w) * wr[7];
+      }
+    }
+    acc = rbf(acc);
+    wav[i] = fminf(1.f, fmaxf(-1.f, acc));
+  }
+}
+
+}  // namespace
+
+// =================================================================================================
+struct q3_codec {
+  q3_codec_cfg cfg;
+  std::map<std::string, DevTensor> t;
+  std::vector<void*> allocs;
+  bf16* buf[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t buf_elems = 0;
+  int* codes_i32 = nullptr;
+  bool finalized = false;
+  int total_up = 1;
+  int launches = 0;
+
+  int alloc_bytes(void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) return q3_set_err("cudaMalloc(%zu B) failed: %s", bytes, cudaGetErrorString(e));
+    allocs.push_back(*p);
+    return 0;
+  }
+  const DevTensor* get(const std::string& n) const {
+    auto it = t.find(n);
+    return it == t.end() ? nullptr : &it->second;
+  }
+};
+
+extern "C" int q3_codec_create(const q3_codec_cfg* cfg, q3_codec** out) {
+  Q3_REQUIRE(cfg && out, "null argument");
+  Q3_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  Q3_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  Q3_REQUIRE(prop.major == 10, "this library is built for sm_100a (B200); device is sm_%d%d", prop.major, prop.minor);
+  Q3_REQUIRE(cfg->head_dim % 2 == 0 && cfg->head_dim <= 64, "codec head_dim must be even and <= 64");
+  Q3_REQUIRE(cfg->sliding_window <= 96, "sliding_window > 96 unsupported");
+  Q3_REQUIRE(cfg->num_heads == cfg->num_kv_heads, "codec transformer is MHA in the reference config");
+  Q3_REQUIRE(cfg->codebook_dim % 32 == 0 && cfg->latent_dim % 16 == 0 && cfg->hidden_size % 16 == 0 &&
+                 cfg->intermediate_size % 16 == 0 && cfg->decoder_dim % 16 == 0,
+             "channel counts must be multiples of 16");
+  if (gemm_init()) return 1;
+  q3_codec* c = new q3_codec();
+  c->cfg = *cfg;
+  c->total_up = 1;
+  for (int i = 0; i < cfg->n_upsample_rates; ++i) c->total_up *= cfg->upsample_rates[i];
+  for (int i = 0; i < cfg->n_upsampling_ratios; ++i) c->total_up *= cfg->upsampling_ratios[i];
+  Q3_REQUIRE((cfg->decoder_dim >> cfg->n_upsample_rates) % 16 == 0, "final channel count must be a multiple of 16");
+  *out = c;
+  return 0;
+}
+
+extern "C" void q3_codec_destroy(q3_codec* c) {
+  if (!c) return;
+  for (void* p : c->allocs) cudaFree(p);
+  delete c;
+}
+
+extern "C" int q3_codec_total_upsample(q3_codec* c) { return c ? c->total_up : 0; }
+
+// Engine-native tensors (converted from the reference state_dict by the Python host):
+// shape[] / ndim describe the tensor; dtype is inferred from the name suffix: names ending in ".w" / "table" /
+// "proj" / "norm" / "ln1" / "ln2" / "cos" / "sin" are bf16, everything else fp32.
+static bool name_is_bf16(const std::string& n) {
+  auto ends = [&](const char* s) { size_t l = strlen(s); return n.size() >= l && n.compare(n.size() - l, l, s) == 0; };
+  if (ends(".dw.w") || ends("dec.out.w")) return false;
+  return ends(".w") || ends(".table") || ends(".proj") || ends(".norm") || ends(".ln1") || ends(".ln2") || ends(".cos") ||
+         ends(".sin");
+}
+
+extern "C" int q3_codec_load_tensor(q3_codec* c, const char* name, const void* dev, const int64_t* shape, int32_t ndim) {
+  Q3_REQUIRE(c && name && dev && shape, "null argument");
+  Q3_CUDA(cudaSetDevice(c->cfg.device));
+  int64_t n = 1;
+  for (int i = 0; i < ndim; ++i) n *= shape[i];
+  DevTensor d;
+  d.dtype = name_is_bf16(name) ? 0 : 1;
+  d.numel = n;
+  const size_t bytes = (size_t)n * (d.dtype == 0 ? 2 : 4);
+  if (c->alloc_bytes(&d.p, (bytes + 255) & ~(size_t)255)) return 1;
+  Q3_CUDA(cudaMemcpy(d.p, dev, bytes, cudaMemcpyDeviceToDevice));
+  c->t[name] = d;
+  return 0;
+}
+
+#define NEED(var, nm, cnt)                                                                          \
+  const DevTensor* var = c->get(nm);                                                                \
+  Q3_REQUIRE(var, "codec: missing tensor %s", std::string(nm).c_str());                             \
+  Q3_REQUIRE(var->numel == (int64_t)(cnt), "codec: tensor %s has %lld elements, expected %lld",     \
+             std::string(nm).c_str(), (long long)var->numel, (long long)(cnt))
+
+static int kpad(int k) { return (k + 63) / 64 * 64; }
+
+extern "C" int q3_codec_finalize(q3_codec* c) {
+  Q3_REQUIRE(c, "null codec");
+  const q3_codec_cfg& g = c->cfg;
+  // spot-check the tensors whose absence would otherwise only surface mid-forward
+  {
+    NEED(a, "rvq.table", (int64_t)g.num_quantizers * g.codebook_size * (g.codebook_dim / 2));
+    NEED(b, "rvq.proj", (int64_t)g.codebook_dim * kpad(g.codebook_dim));
+    NEED(d, "dec.out.w", (int64_t)7 * (g.decoder_dim >> g.n_upsample_rates));
+    (void)a; (void)b; (void)d;
+  }
+  c->finalized = true;
+  return 0;
+}
+
+namespace {
+
+struct Runner {
+  q3_codec* c;
+  cudaStream_t stream;
+  int B;
+  int err = 0;
+
+  static int pick_bn(int N, int mtiles, int B) {
+    static const int cand[] = {256, 240, 224, 208, 192, 176, 160, 144, 128, 112, 96, 80, 64};
+    int best_small = 0;
+    for (int bn : cand) {
+      if (N % bn) continue;
+      if ((long long)mtiles * (N / bn) * B >= 148) return bn;
+      best_small = bn;
+    }
+    if (best_small) return best_small;
+    for (int bn : cand) if (bn <= N) return bn;
+    return N;  // N < 64 (multiple of 16)
+  }
+
+  // one tap-GEMM: a [B][T][K] -> [B][T][N]
+  void gemm(const bf16* a, int T, int K, const char* wname, int N, int ntaps, const int* shifts, GemmEpilogue ep) {
+    if (err) return;
+    const DevTensor* w = c->get(wname);
+    const int Kp = kpad(K);
+    if (!w || w->numel != (int64_t)N * ntaps * Kp) {
+      err = q3_set_err("codec: tensor %s missing or wrong size (want %lld)", wname, (long long)N * ntaps * Kp);
+      return;
+    }
+    if (ep.cmod == 0) ep.cmod = N;
+    GemmPlan plan;
+    const int mt = (T + 127) / 128;
+    if (gemm_make_plan(&plan, a, B, T, K, K, (int64_t)T * K, reinterpret_cast<const bf16*>(w->p), N, Kp, ntaps, shifts,
+                       pick_bn(N, mt, B), ep)) { err = 1; return; }
+    if (gemm_launch(plan, stream)) { err = 1; return; }
+    c->launches++;
+  }
+  const float* f32(const std::string& n, int64_t cnt) {
+    const DevTensor* d = c->get(n);
+    if (!d || d->numel != cnt || d->dtype != 1) { if (!err) err = q3_set_err("codec: fp32 tensor %s missing/wrong size", n.c_str()); return nullptr; }
+    return reinterpret_cast<const float*>(d->p);
+  }
+  const bf16* b16(const std::string& n, int64_t cnt) {
+    const DevTensor* d = c->get(n);
+    if (!d || d->numel != cnt || d->dtype != 0) { if (!err) err = q3_set_err("codec: bf16 tensor %s missing/wrong size", n.c_str()); return nullptr; }
+    return reinterpret_cast<const bf16*>(d->p);
+  }
+};
+
+}  // namespace
+
+extern "C" int q3_codec_forward(q3_codec* c, const int32_t* codes_dev, int32_t B, int32_t T, float* wav_dev, void* stream_) {
+  Q3_REQUIRE(c && c->finalized, "codec not finalized");
+  Q3_REQUIRE(codes_dev && wav_dev && B >= 1 && T >= 1, "bad arguments");
+  Q3_REQUIRE(T <= c->cfg.max_frames, "T=%d exceeds max_frames=%d", T, c->cfg.max_frames);
+  const q3_codec_cfg& g = c->cfg;
+  Q3_CUDA(cudaSetDevice(g.device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int Cl = g.latent_dim, Hh = g.hidden_size, nh = g.num_heads, hd = g.head_dim, I = g.intermediate_size;
+  const int Cfin = g.decoder_dim >> g.n_upsample_rates;
+  // per-(b,frame) element high-water mark over all stages
+  size_t per_frame = std::max<size_t>({(size_t)3 * nh * hd, (size_t)2 * I, (size_t)Cl});
+  {
+    size_t up = 1;
+    for (int i = 0; i < g.n_upsampling_ratios; ++i) { up *= g.upsampling_ratios[i]; per_frame = std::max(per_frame, up * 4 * Cl); }
+    per_frame = std::max(per_frame, up * (size_t)g.decoder_dim);
+    int ch = g.decoder_dim;
+    for (int i = 0; i < g.n_upsample_rates; ++i) { up *= g.upsample_rates[i]; ch /= 2; per_frame = std::max(per_frame, up * (size_t)ch); }
+  }
+  const size_t need = per_frame * (size_t)B * T;
+  if (need > c->buf_elems) {
+    for (int i = 0; i < 4; ++i) {
+      void* p;
+      if (c->alloc_bytes(&p, need * 2 + 1024)) return 1;
+      c->buf[i] = reinterpret_cast<bf16*>(p);
+    }
+    c->buf_elems = need;
+  }
+  bf16 *X = c->buf[0], *Y = c->buf[1], *Z = c->buf[2], *W = c->buf[3];
+  Runner R{c, stream, B};
+  c->launches = 0;
+  const int zero = 0;
+  GemmEpilogue none{};
+
+  // ---- RVQ decode -> [B][T][codebook_dim]
+  const int D = g.codebook_dim / 2;
+  rvq_gather_kernel<<<B * T, 128, 0, stream>>>(codes_dev, R.b16("rvq.table", (int64_t)g.num_quantizers * g.codebook_size * D), X, B,
+                                               g.num_quantizers, T, D, g.codebook_size);
+  c->launches++;
+  if (R.err) return 1;
+  { GemmEpilogue e = none; e.out_raw = Y; R.gemm(X, T, g.codebook_dim, "rvq.proj", g.codebook_dim, 1, &zero, e); }
+  // ---- pre_conv k=3 (…v2.py:839-843,874)
+  { const int sh[3] = {-2, -1, 0}; GemmEpilogue e = none; e.bias = R.f32("pre_conv.b", Cl); e.out_raw = X;
+    R.gemm(Y, T, g.codebook_dim, "pre_conv.w", Cl, 3, sh, e); }
+  // ---- pre_transformer (…v2.py:501-575)
+  { GemmEpilogue e = none; e.bias = R.f32("tr.in.b", Hh); e.out_raw = Y; R.gemm(X, T, Cl, "tr.in.w", Hh, 1, &zero, e); }
+  bf16* xres = Y;  // residual stream [B][T][Hh]
+  const int rows = B * T;
+  for (int l = 0; l < g.num_layers && !R.err; ++l) {
+    const std::string p = "tr." + std::to_string(l);
+    rmsnorm_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(xres, R.b16(p + ".ln1", Hh), X, rows, Hh, g.rms_eps);
+    { GemmEpilogue e = none; e.out_raw = Z; R.gemm(X, T, Hh, (p + ".qkv.w").c_str(), 3 * nh * hd, 1, &zero, e); }
+    rope_qk_kernel<<<296, 256, 0, stream>>>(Z, R.b16("rope.cos", (int64_t)g.max_frames * (hd / 2)),
+                                            R.b16("rope.sin", (int64_t)g.max_frames * (hd / 2)), B, T, nh, hd);
+    swa_attention_kernel<<<(rows * nh + 7) / 8, 256, 0, stream>>>(Z, X, B, T, nh, hd, g.sliding_window);
+    { GemmEpilogue e = none; e.scale = R.f32(p + ".ls1", Hh); e.resid = xres; e.out_raw = W;
+      R.gemm(X, T, nh * hd, (p + ".o.w").c_str(), Hh, 1, &zero, e); }
+    rmsnorm_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(W, R.b16(p + ".ln2", Hh), X, rows, Hh, g.rms_eps);
+    { GemmEpilogue e = none; e.act = ACT_SWIGLU_PAIR; e.out_act = Z; R.gemm(X, T, Hh, (p + ".gate_up.w").c_str(), 2 * I, 1, &zero, e); }
+    { GemmEpilogue e = none; e.scale = R.f32(p + ".ls2", Hh); e.resid = W; e.out_raw = xres;
+      R.gemm(Z, T, I, (p + ".down.w").c_str(), Hh, 1, &zero, e); }
+    c->launches += 4;
+  }
+  rmsnorm_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(xres, R.b16("tr.norm", Hh), X, rows, Hh, g.rms_eps);
+  c->launches++;
+  { GemmEpilogue e = none; e.bias = R.f32("tr.out.b", Cl); e.out_raw = Z; R.gemm(X, T, Hh, "tr.out.w", Cl, 1, &zero, e); }
+  // ---- upsample: ConvT(k=s=f) + ConvNeXt (…v2.py:845-855,878-880)
+  bf16* cur = Z;  // [B][Tc][Cl]
+  int Tc = T;
+  for (int i = 0; i < g.n_upsampling_ratios && !R.err; ++i) {
+    const int f = g.upsampling_ratios[i];
+    const std::string p = "up." + std::to_string(i);
+    bf16* u = (cur == Z) ? Y : Z;
+    { GemmEpilogue e = none; e.bias = R.f32(p + ".ct.b", Cl); e.cmod = Cl; e.out_raw = u;
+      R.gemm(cur, Tc, Cl, (p + ".ct.w").c_str(), f * Cl, 1, &zero, e); }
+    Tc *= f;
+    const float *dww = R.f32(p + ".dw.w", (int64_t)Cl * 7), *dwb = R.f32(p + ".dw.b", Cl), *lw = R.f32(p + ".ln_g", Cl),
+                *lb = R.f32(p + ".ln_beta", Cl);
+    if (R.err) break;
+    dwconv_ln_kernel<<<B * Tc, 256, (Cl + 64) * sizeof(float), stream>>>(u, dww, dwb, lw, lb, X, B, Tc, Cl);
+    c->launches++;
+    { GemmEpilogue e = none; e.bias = R.f32(p + ".pw1.b", 4 * Cl); e.act = ACT_GELU; e.out_act = W;
+      R.gemm(X, Tc, Cl, (p + ".pw1.w").c_str(), 4 * Cl, 1, &zero, e); }
+    bf16* o = (u == Y) ? Z : Y;
+    { GemmEpilogue e = none; e.bias = R.f32(p + ".pw2.b", Cl); e.scale = R.f32(p + ".gamma", Cl); e.resid = u; e.out_raw = o;
+      R.gemm(W, Tc, 4 * Cl, (p + ".pw2.w").c_str(), Cl, 1, &zero, e); }
+    cur = o;
+  }
+  // ---- decoder.0: conv k7 latent -> decoder_dim; epilogue applies block 0's SnakeBeta (…v2.py:857,646)
+  int C = g.decoder_dim;
+  bf16* act = X;  // snake-activated input of the next conv
+  {
+    const int sh[7] = {-6, -5, -4, -3, -2, -1, 0};
+    GemmEpilogue e = none; e.bias = R.f32("dec.in.b", C); e.act = ACT_SNAKE; e.snake_ea = R.f32("dec.0.snake_ea", C);
+    e.snake_ib = R.f32("dec.0.snake_ib", C); e.out_act = act;
+    R.gemm(cur, Tc, Cl, "dec.in.w", C, 7, sh, e);
+  }
+  // ---- decoder blocks (…v2.py:638-658, :619-635)
+  bf16 *y = Y, *tmp = Z, *act2 = W;
+  for (int bi = 0; bi < g.n_upsample_rates && !R.err; ++bi) {
+    const int r = g.upsample_rates[bi];
+    const int Co = C / 2;
+    const std::string p = "dec." + std::to_string(bi);
+    {
+      const int sh[2] = {0, -1};
+      GemmEpilogue e = none; e.bias = R.f32(p + ".ct.b", Co); e.cmod = Co; e.out_raw = y; e.act = ACT_SNAKE;
+      e.snake_ea = R.f32(p + ".0.s1_ea", Co); e.snake_ib = R.f32(p + ".0.s1_ib", Co); e.out_act = act2;
+      R.gemm(act, Tc, C, (p + ".ct.w").c_str(), r * Co, 2, sh, e);
+    }
+    Tc *= r;
+    C = Co;
+    std::swap(act, act2);  // act now holds snake1(y)
+    for (int u = 0; u < 3 && !R.err; ++u) {
+      const int dil = u == 0 ? 1 : (u == 1 ? 3 : 9);
+      const std::string q = p + "." + std::to_string(u);
+      {
+        int sh[7];
+        for (int j = 0; j < 7; ++j) sh[j] = -(6 - j) * dil;
+        GemmEpilogue e = none; e.bias = R.f32(q + ".c1.b", C); e.act = ACT_SNAKE; e.snake_ea = R.f32(q + ".s2_ea", C);
+        e.snake_ib = R.f32(q + ".s2_ib", C); e.out_act = tmp;
+        R.gemm(act, Tc, C, (q + ".c1.w").c_str(), C, 7, sh, e);
+      }
+      {
+        // next activation: next unit's act1, or the next block's leading snake, or the final snake
+        std::string nx = (u < 2) ? (p + "." + std::to_string(u + 1) + ".s1")
+                                 : (bi + 1 < g.n_upsample_rates ? ("dec." + std::to_string(bi + 1) + ".snake") : std::string("dec.out.snake"));
+        GemmEpilogue e = none; e.bias = R.f32(q + ".c2.b", C); e.resid = y; e.out_raw = act2 /*new y*/; e.act = ACT_SNAKE;
+        e.snake_ea = R.f32(nx + "_ea", C); e.snake_ib = R.f32(nx + "_ib", C); e.out_act = act;
+        // out_act overwrites `act` (this GEMM's input is tmp, its residual is y) — safe
+        R.gemm(tmp, Tc, C, (q + ".c2.w").c_str(), C, 1, &zero, e);
+        std::swap(y, act2);  // y <- new residual stream
+      }
+    }
+  }
+  if (R.err) return 1;
+  // ---- final conv + clamp
+  {
+    const float* w = R.f32("dec.out.w", (int64_t)7 * Cfin);
+    const float* bsrc = R.f32("dec.out.b", 1);
+    if (R.err) return 1;
+    float bias_h = 0.f;
+    Q3_CUDA(cudaMemcpyAsync(&bias_h, bsrc, sizeof(float), cudaMemcpyDeviceToHost, stream));
+    Q3_CUDA(cudaStreamSynchronize(stream));
+    final_conv_kernel<<<1184, 256, 0, stream>>>(act, w, bias_h, wav_dev, B, Tc, Cfin);
+    c->launches++;
+  }
+  Q3_CUDA(cudaGetLastError());
+  return R.err;
+}

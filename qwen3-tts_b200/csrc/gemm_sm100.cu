@@ -1,0 +1,291 @@
+// tcgen05 tap-GEMM kernel (see gemm_sm100.cuh).  Warp-specialised, one 128 x bn output tile per CTA:
+//   warp 0  : TMA producer (A tile via a 3-D map with a per-tap row shift, W tile via a 2-D map), 4-stage ring
+//   warp 1  : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=bn, K=16, bf16 -> fp32 in TMEM)
+//   warps 2-5: epilogue — tcgen05.ld the accumulator (one output row per thread), fused bias / LayerScale /
+//              residual / SnakeBeta / GELU / SwiGLU, bf16 stores.
+#include "gemm_sm100.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;        // 16 KB
+constexpr int B_BYTES_MAX = 256 * BK * 2;   // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (clock64() - t0 > 4000000000LL) __trap();  // never hang the box on a protocol bug
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"): 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);        // start address
+  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset
+  d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_constant__ GemmPlan p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // full[S], empty[S], tmem_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * p.bn, b = blockIdx.z;
+  const int kpb = p.Kp / BK;
+  const int nkb = p.ntaps * kpb;
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
+  const uint32_t b_bytes = (uint32_t)p.bn * BK * 2;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)p.bn) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmW) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        if (kb >= STAGES) mbar_wait(empty0 + 8 * s, ((kb / STAGES) - 1) & 1);
+        const int tap = kb / kpb, k0 = (kb - tap * kpb) * BK;
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+        mbar_expect_tx(full0 + 8 * s, A_BYTES + b_bytes);
+        tma_load_3d(sa, &p.tmA, k0, m0 + p.shift[tap], b, full0 + 8 * s);
+        tma_load_2d(sb, &p.tmW, tap * p.Kp + k0, n0, full0 + 8 * s);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N=bn, M=128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+        const uint64_t ad = make_sdesc(sa), bd = make_sdesc(sb);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) start-address field
+          umma_bf16(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        }
+        umma_commit(empty0 + 8 * s);          // frees the smem slot once these MMAs have read it
+        if (kb == nkb - 1) umma_commit(tfull);  // accumulator complete
+      }
+    }
+  } else {
+    // ---- epilogue: warp (w % 4) owns TMEM lanes [32*(w%4), +32); thread = one output row
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    mbar_wait(tfull, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const GemmEpilogue& E = p.ep;
+    const bool row_ok = m < p.T;
+    const size_t row_off = ((size_t)b * p.T + (row_ok ? m : 0)) * (size_t)p.N;
+    for (int c0 = 0; c0 < p.bn; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int n = n0 + c0;
+      if (!row_ok || n >= p.N) continue;
+      float x[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
+      int ch = n % E.cmod;
+      if (E.bias) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] += E.bias[ch + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = rbf(x[i]);  // the reference's layer output is bf16
+      if (E.scale) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = rbf(x[i] * E.scale[ch + i]);
+      }
+      if (E.resid) {
+        const uint4 r0 = *reinterpret_cast<const uint4*>(E.resid + row_off + n);
+        const uint4 r1 = *reinterpret_cast<const uint4*>(E.resid + row_off + n + 8);
+        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { x[2 * i] = rbf(x[2 * i] + bf16lo(rr[i])); x[2 * i + 1] = rbf(x[2 * i + 1] + bf16hi(rr[i])); }
+      }
+      if (E.out_raw) {
+        uint4 o0, o1;
+        o0.x = pack_bf16(x[0], x[1]); o0.y = pack_bf16(x[2], x[3]); o0.z = pack_bf16(x[4], x[5]); o0.w = pack_bf16(x[6], x[7]);
+        o1.x = pack_bf16(x[8], x[9]); o1.y = pack_bf16(x[10], x[11]); o1.z = pack_bf16(x[12], x[13]); o1.w = pack_bf16(x[14], x[15]);
+        *reinterpret_cast<uint4*>(E.out_raw + row_off + n) = o0;
+        *reinterpret_cast<uint4*>(E.out_raw + row_off + n + 8) = o1;
+      }
+      if (E.out_act) {
+        if (E.act == ACT_SWIGLU_PAIR) {
+          // columns (2i, 2i+1) = (gate_i, up_i)
+          float y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float g = x[2 * i], u = x[2 * i + 1];
+            y[i] = rbf(g / (1.f + __expf(-g))) * u;
+          }
+          uint4 o;
+          o.x = pack_bf16(y[0], y[1]); o.y = pack_bf16(y[2], y[3]); o.z = pack_bf16(y[4], y[5]); o.w = pack_bf16(y[6], y[7]);
+          *reinterpret_cast<uint4*>(E.out_act + ((size_t)b * p.T + m) * (size_t)(p.N / 2) + n / 2) = o;
+        } else {
+          float y[16];
+          if (E.act == ACT_SNAKE) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float sn = sinf(x[i] * E.snake_ea[ch + i]);
+              y[i] = x[i] + E.snake_ib[ch + i] * sn * sn;
+            }
+          } else if (E.act == ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] = gelu_erf(x[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) y[i] = x[i];
+          }
+          uint4 o0, o1;
+          o0.x = pack_bf16(y[0], y[1]); o0.y = pack_bf16(y[2], y[3]); o0.z = pack_bf16(y[4], y[5]); o0.w = pack_bf16(y[6], y[7]);
+          o1.x = pack_bf16(y[8], y[9]); o1.y = pack_bf16(y[10], y[11]); o1.z = pack_bf16(y[12], y[13]); o1.w = pack_bf16(y[14], y[15]);
+          *reinterpret_cast<uint4*>(E.out_act + row_off + n) = o0;
+          *reinterpret_cast<uint4*>(E.out_act + row_off + n + 8) = o1;
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn g_encode = nullptr;
+
+}  // namespace
+
+int gemm_init() {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    Q3_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    Q3_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
+    g_encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  Q3_CUDA(cudaFuncSetAttribute(tap_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  return 0;
+}
+
+int gemm_make_plan(GemmPlan* plan, const bf16* a, int B, int T, int K, int64_t lda, int64_t a_batch_stride, const bf16* w,
+                   int N, int Kp, int ntaps, const int* shifts, int bn, const GemmEpilogue& ep) {
+  Q3_REQUIRE(g_encode, "gemm_init() not called");
+  Q3_REQUIRE(Kp % BK == 0 && Kp >= K, "Kp must be a multiple of 64 and >= K");
+  Q3_REQUIRE(bn % 16 == 0 && bn >= 16 && bn <= 256, "bn must be a multiple of 16 in [16,256]");
+  Q3_REQUIRE(N % 16 == 0, "N must be a multiple of 16");
+  Q3_REQUIRE(ntaps >= 1 && ntaps <= 8, "ntaps out of range");
+  Q3_REQUIRE((lda * 2) % 16 == 0 && (a_batch_stride * 2) % 16 == 0 && ((uintptr_t)a % 16) == 0, "A alignment");
+  memset(plan, 0, sizeof(*plan));
+  plan->B = B; plan->T = T; plan->N = N; plan->Kp = Kp; plan->ntaps = ntaps; plan->bn = bn; plan->ep = ep;
+  for (int i = 0; i < ntaps; ++i) plan->shift[i] = shifts[i];
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)lda * 2, (cuuint64_t)a_batch_stride * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BM, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = g_encode(&plan->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)a, dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    Q3_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed: %d (K=%d T=%d B=%d lda=%lld)", (int)r, K, T, B, (long long)lda);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)ntaps * Kp, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)ntaps * Kp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)bn};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = g_encode(&plan->tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    Q3_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(W) failed: %d (N=%d Kp=%d taps=%d)", (int)r, N, Kp, ntaps);
+  }
+  return 0;
+}
+
+int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
+  dim3 grid((plan.T + BM - 1) / BM, (plan.N + plan.bn - 1) / plan.bn, plan.B);
+  tap_gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(plan);
+  Q3_CUDA(cudaGetLastError());
+  return 0;
+}

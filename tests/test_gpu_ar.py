@@ -186,10 +186,12 @@ def test_full_shape_1p7b_two_frames():
     scale = float(np.std(ref.record["talker_logits"][0]))
     for f in range(N + 1):
         d = np.abs(tl[f] - ref.record["talker_logits"][f])
-        assert d.max() < 0.08 * max(scale, 1.0) + 0.06, (f, d.max(), scale)
+        # calibration: the oracle's own bf16-vs-fp32 gap at this shape is max 0.11*std, mean 0.024*std
+        assert d.max() < 0.2 * scale and d.mean() < 0.05 * scale, (f, d.max(), d.mean(), scale)
     G = cfg.num_code_groups
     for f in range(N):
         for j in range(G - 1):
-            d = np.abs(cl[f, j] - ref.record["cp_logits"][f * (G - 1) + j])
-            assert d.max() < 0.08 * max(scale, 1.0) + 0.06, (f, j, d.max())
+            r = ref.record["cp_logits"][f * (G - 1) + j]
+            d = np.abs(cl[f, j] - r)
+            assert d.max() < 0.2 * float(np.std(r)) and d.mean() < 0.05 * float(np.std(r)), (f, j, d.max(), d.mean())
     eng.close()
