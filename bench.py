@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — hot-path benchmark of the B200-native Qwen3-TTS engine (contract: see the task statement).
+
+One "step" = one pass of the hot path over one batch of synthetic utterances of the configuration BASELINE.json
+quotes the metric on (config[2]: Qwen3-TTS-12Hz-1.7B CustomVoice, batch 8, non-streaming):
+    prefill (8 prompts, L_i = T_i + 11 [+12 instruct on odd rows], T_i in 16..72)  ->
+    125 frame-steps of the fused AR kernel (15 code-predictor passes + 28 talker layers + sampling each)  ->
+    codec decode of the 8 x 125 frames to 24 kHz waveform.
+metric = speech tokens (12.5 Hz frames; x16 for individual codebook tokens) per second, whole job.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+N > 1 is launched by torchrun (one rank per GPU, independent replicas = weak scaling, NCCL only for the
+barrier / max-over-ranks reduction).  `--impl reference` times the reference's CPU path (oracle port driving
+the restated loop — the HF generate loop cannot run under transformers 5.5.0) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+FRAME_SEC = 0.08
+
+
+def usable_cores():
+    """Cores this process may really use: affinity mask capped by the cgroup CPU quota (a 128-CPU host can
+    hand a container an 8-core quota; 128 threads on that quota thrash)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, min(n, 64))
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--frames", type=int, default=125)
+    ap.add_argument("--model", default="1.7b", choices=["1.7b", "0.6b", "tiny"])
+    ap.add_argument("--greedy", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=2)
+    return ap.parse_args()
+
+
+def workload(args, H):
+    """Synthetic inputs of config[2]'s shape: seeded, bf16, pinned host memory."""
+    B = args.batch
+    lens = []
+    for i in range(B):
+        T = 16 + 8 * (i % 8)
+        lens.append(T + 11 + (12 if i % 2 else 0))
+    embs, trail = [], []
+    for i, L in enumerate(lens):
+        g = torch.Generator().manual_seed(1000 + i)
+        embs.append((torch.randn(L, H, generator=g) * 0.5).to(torch.bfloat16).pin_memory())
+        trail.append(torch.zeros(0, H, dtype=torch.bfloat16))
+    g = torch.Generator().manual_seed(999)
+    pad = (torch.randn(H, generator=g) * 0.1).to(torch.bfloat16).pin_memory()
+    return lens, embs, trail, pad
+
+
+def model_cfg(name):
+    from qwen3_tts_b200 import synthetic
+    return {"1.7b": synthetic.cfg_1p7b, "0.6b": synthetic.cfg_0p6b, "tiny": synthetic.cfg_tiny}[name]()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_step(Wcpu, Ccpu, ocfg, ccfg, embs, trail, pad, sp_kwargs, n_frames, full_frames):
+    """One bounded sample of the workload on the host: prefill + n_frames frame-steps + codec decode of n_frames
+    frames, extrapolated to the full `full_frames` utterance.  Returns (frames_per_s, detail)."""
+    from oracle import talker as OT, codec as OC
+    e32 = [e.float() for e in embs]
+    t32 = [t.float() for t in trail]
+    sp0 = OT.SamplingCfg(max_new_tokens=1, suppress_eos=True, **sp_kwargs)
+    t0 = time.perf_counter()
+    OT.generate(Wcpu, ocfg, e32, t32, pad.float(), sp0)
+    t_pre = time.perf_counter() - t0
+    spn = OT.SamplingCfg(max_new_tokens=n_frames + 1, suppress_eos=True, **sp_kwargs)
+    t0 = time.perf_counter()
+    r = OT.generate(Wcpu, ocfg, e32, t32, pad.float(), spn)
+    t_all = time.perf_counter() - t0
+    per_frame = max(t_all - t_pre, 1e-9) / n_frames
+    codes = torch.stack(r.codes).transpose(1, 2).contiguous()  # (B,16,n)
+    t0 = time.perf_counter()
+    OC.decoder_forward(Ccpu, ccfg, codes)
+    t_codec = (time.perf_counter() - t0) / n_frames
+    B = len(embs)
+    total = t_pre + full_frames * (per_frame + t_codec)
+    return B * full_frames / total, {"prefill_s": t_pre, "per_frame_s": per_frame, "codec_per_frame_s": t_codec}
+
+
+def to_oracle_cfgs(cfg, ccfg):
+    from oracle import talker as OT, codec as OC
+    st = lambda s: OT.StackCfg(s.hidden_size, s.num_layers, s.num_heads, s.num_kv_heads, s.head_dim,  # noqa: E731
+                               s.intermediate_size, s.vocab_size, s.rms_eps, s.rope_theta)
+    o = OT.TTSCfg(talker=st(cfg.talker), cp=st(cfg.cp), num_code_groups=cfg.num_code_groups,
+                  codec_eos_token_id=cfg.codec_eos_token_id)
+    oc = OC.CodecCfg(**{k: getattr(ccfg, k) for k in OC.CodecCfg.__dataclass_fields__})
+    return o, oc
+
+
+def sampling_kwargs(args):
+    if args.greedy:
+        return dict(do_sample=False, subtalker_dosample=False)
+    return dict(do_sample=True, top_k=50, top_p=1.0, temperature=0.9, repetition_penalty=1.05, subtalker_dosample=True,
+                subtalker_top_k=50, subtalker_top_p=1.0, subtalker_temperature=0.9)
+
+
+def config_block(args, lens, n_gpus):
+    return {"workload": f"Qwen3-TTS-12Hz-{args.model.upper()} CustomVoice-shaped, batch {args.batch}/GPU, non-streaming, "
+                        f"{args.frames} frames/utterance, prefill+AR decode+codec decode",
+            "batch_per_gpu": args.batch, "global_batch": args.batch * n_gpus, "frames": args.frames, "prompt_lens": lens,
+            "sampling": "greedy" if args.greedy else "do_sample top_k=50 T=0.9 rep=1.05 (reference defaults)",
+            "weights": "seeded random, expected shipped shapes (no checkpoints offline)",
+            "parallelism": f"dp{n_gpus} (independent replicas, no data-path collective)",
+            "l2": "per-step weight stream (>=3 GB) exceeds the 126 MB L2: no flush needed"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.manual_seed(0)
+
+    import qwen3_tts_b200 as q
+    from qwen3_tts_b200 import synthetic
+    cfg = model_cfg(args.model)
+    ccfg = q.CodecConfig() if args.model != "tiny" else q.CodecConfig(
+        codebook_size=64, codebook_dim=64, hidden_size=64, latent_dim=64, num_heads=4, num_kv_heads=4, head_dim=16,
+        sliding_window=6, intermediate_size=96, num_layers=2, decoder_dim=256)
+    H = cfg.talker.hidden_size
+    lens, embs, trail, pad = workload(args, H)
+    spk = sampling_kwargs(args)
+    ncores = usable_cores()
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        torch.set_num_threads(ncores)
+        Wg = synthetic.random_tts_weights(cfg, device="cpu", seed=0, dtype=torch.bfloat16)
+        Wcpu = {k: v.float() for k, v in Wg.items()}
+        Ccpu = {k: v.to(torch.bfloat16).float() for k, v in synthetic.random_codec_weights(ccfg, device="cpu", seed=0).items()}
+        ocfg, occfg = to_oracle_cfgs(cfg, ccfg)
+        vals = []
+        t_begin = time.perf_counter()
+        for i in range(args.warmup + args.steps):
+            v, det = cpu_reference_step(Wcpu, Ccpu, ocfg, occfg, embs, trail, pad, spk, args.cpu_frames, args.frames)
+            if i >= args.warmup:
+                vals.append(v)
+        wall = time.perf_counter() - t_begin
+        val = float(np.mean(vals))
+        sample = (f"per step: prefill B={args.batch} + {args.cpu_frames} frame-steps + codec decode of {args.cpu_frames} frames, "
+                  f"fp32, {ncores} threads, extrapolated to {args.frames} frames")
+        out = {"impl": "reference", "metric": "speech_tokens_per_s", "value": val, "unit": "frames/s (12.5 Hz speech tokens)",
+               "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": 1000.0 * args.batch * args.frames / val, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_block(args, lens, 1),
+               "rtf": 1.0 / (val * FRAME_SEC) * 1.0,
+               "cpu_baseline": {"value": val, "unit": "frames/s", "cores": ncores, "kind": "port", "sample": sample, **det},
+               "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "gpu_launches": 0, "wall_s": wall}
+        print(json.dumps(out))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
+    dev = f"cuda:{local}"
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    from qwen3_tts_b200.pipeline import TTSEngine
+    W = synthetic.random_tts_weights(cfg, device=dev, seed=0)
+    CW = synthetic.random_codec_weights(ccfg, device=dev, seed=0)
+    max_ctx = max(lens) + args.frames + 8
+    eng = TTSEngine(cfg, W, ccfg, CW, device=dev, max_batch=max(args.batch, 1), max_ctx=max_ctx,
+                    codec_max_frames=max(args.frames + 8, 64))
+    sp = q.SamplingParams(max_new_tokens=args.frames + 1, suppress_eos=True, seed=1234, **spk)
+    B, N, G = args.batch, args.frames, cfg.num_code_groups
+    d_embs = [e.to(dev) for e in embs]
+    d_trail = [t.to(dev) for t in trail]
+    d_pad = pad.to(dev)
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    t_pre = t_dec = t_cod = 0.0
+
+    def step_resident(timed):
+        nonlocal t_pre, t_dec, t_cod
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        e0.record(stream)
+        eng.ar.prefill(d_embs, d_trail, d_pad, sp)
+        codes = torch.zeros(B, N, G, dtype=torch.int32, device=dev)
+        e1.record(stream)
+        eng.ar.decode(N, codes)
+        e2.record(stream)
+        wav = eng.codec.chunked_decode(codes.transpose(1, 2))
+        e3.record(stream)
+        if timed:
+            torch.cuda.synchronize()
+            t_pre += e0.elapsed_time(e1); t_dec += e1.elapsed_time(e2); t_cod += e2.elapsed_time(e3)
+        return wav
+
+    for _ in range(args.warmup):
+        step_resident(False)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    s0, s1 = ev(), ev()
+    s0.record(stream)
+    for _ in range(args.steps):
+        wav = step_resident(True)
+    s1.record(stream)
+    barrier()
+    ms_total = s0.elapsed_time(s1)
+    clk = clocks.stop()
+    fd, n_valid, _ = eng.ar.progress()
+    assert fd == N and all(v == N for v in n_valid), (fd, n_valid)
+    assert torch.isfinite(wav).all()
+
+    # ---- end-to-end through the public call: pinned host inputs, H2D + D2H inside the timed region
+    for _ in range(2):
+        eng.synthesize(embs, trail, pad, sp)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        wavs_host, _ = eng.synthesize(embs, trail, pad, sp)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = sum(e.numel() * 2 for e in embs) + pad.numel() * 2
+    d2h = sum(w.size * 4 for w in wavs_host)
+
+    tms = torch.tensor([ms_total, e2e_s * 1000.0, t_dec], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms, t_dec_max = [float(x) for x in tms.tolist()]
+    frames_total = world * B * N * args.steps
+    value = frames_total / (ms_total / 1000.0)
+    e2e_val = frames_total / (e2e_ms / 1000.0)
+
+    # ---- roofline of the dominant kernel (fused frame-step kernel): algorithmic bytes / measured duration
+    S_mean = int(np.mean(lens) + N / 2)
+    a_bytes, a_stream = eng.ar.algorithmic_bytes(B, S_mean)
+    t_step = (t_dec / args.steps) / N / 1000.0  # s per frame-step (this rank)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak = 6650.0; peak_src = "fallback 6.65 TB/s (B200_PROFILING.md)"
+    achieved = a_bytes / t_step / 1e9
+    roof = {"bound": "hbm", "kernel": "q3_program_kernel (fused frame-step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+            "algorithmic_bytes_per_launch": a_bytes * N, "algorithmic_bytes_per_frame_step": a_bytes,
+            "no_residency_bytes_per_frame_step": a_stream, "ms_per_frame_step": t_step * 1e3, "mean_context": S_mean}
+
+    out = {"metric": "speech_tokens_per_s", "value": value, "unit": "frames/s (12.5 Hz speech tokens; x16 codebook tokens)",
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+           "config": config_block(args, lens, world), "rtf": (ms_total / 1000.0) / (frames_total * FRAME_SEC),
+           "breakdown_ms_per_step": {"prefill": t_pre / args.steps, "decode": t_dec / args.steps, "codec": t_cod / args.steps},
+           "roofline": roof,
+           "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "rtf": (e2e_ms / 1000.0) / (frames_total * FRAME_SEC)},
+           "gpu_launches": args.steps * (len(range(0, sum(lens), 32)) + 2 + eng.codec.last_launches()),
+           "clocks": clk}
+
+    # ---- reference CPU path beside it (rank 0, N=1 only): bounded sample on the host cores
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(ncores)
+        Wcpu = {k: v.float().cpu() for k, v in W.items()}
+        Ccpu = {k: v.to(torch.bfloat16).float().cpu() for k, v in CW.items()}
+        ocfg, occfg = to_oracle_cfgs(cfg, ccfg)
+        v, det = cpu_reference_step(Wcpu, Ccpu, ocfg, occfg, embs, trail, pad, spk, args.cpu_frames, N)
+        out["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": ncores, "kind": "port",
+                               "sample": f"prefill B={B} + {args.cpu_frames} frame-steps + codec decode of {args.cpu_frames} frames, "
+                                         f"fp32, {ncores} threads, extrapolated to {N} frames", **det}
+    if rank == 0:
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

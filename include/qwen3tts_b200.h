@@ -113,6 +113,12 @@ int q3_get_progress(q3_engine* e, int32_t* frames_done, int32_t* n_valid, int32_
 int q3_set_debug(q3_engine* e, const int32_t* forced_dev, int32_t n_frames, float* talker_logits_dev,
                  float* cp_logits_dev);
 
+/* Profiling hooks (profiles/ + bench --profile): prof_dev = uint64 [n_phases][2] globaltimer ns (phase end,
+ * barrier end) written by CTA 0 for the first frame of each q3_decode; q3_describe_frame_program returns -n_phases
+ * and fills kinds[i] = type*100 + stack*10 + epilogue. */
+int q3_set_profile(q3_engine* e, unsigned long long* prof_dev);
+int q3_describe_frame_program(q3_engine* e, int32_t* kinds, int32_t capacity);
+
 /* Bytes the fused frame-step kernel must stream per step for batch B at mean context S
  * (W_talker + W_cp_unique + B*(S+1)*KV_tok), and the no-residency figure. */
 int q3_algorithmic_bytes(q3_engine* e, int32_t B, int32_t S, double* a_bytes, double* a_stream_bytes);
@@ -144,6 +150,8 @@ int q3_codec_finalize(q3_codec* c);
  * codes: int32 [B][K][T] device; wav: fp32 [B][T*upsample] device.  Asynchronous. */
 int q3_codec_forward(q3_codec* c, const int32_t* codes_dev, int32_t B, int32_t T, float* wav_dev, void* stream);
 int q3_codec_total_upsample(q3_codec* c);
+/* kernels launched by the last q3_codec_forward (bench.py's gpu_launches bookkeeping) */
+int q3_codec_last_launch_count(q3_codec* c);
 
 #ifdef __cplusplus
 }

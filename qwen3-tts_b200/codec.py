@@ -168,6 +168,9 @@ class CodecDecoder:
         self._f("dec.out.w", g(f"decoder.{nb + 2}.conv.weight")[0].t().contiguous())  # [7][C]
         self._f("dec.out.b", g(f"decoder.{nb + 2}.conv.bias"))
 
+    def last_launches(self):
+        return int(self.lib.q3_codec_last_launch_count(self.h))
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.q3_codec_destroy(self.h)

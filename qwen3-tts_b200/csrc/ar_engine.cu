@@ -47,7 +47,17 @@ constexpr int MAXCOLS = 32;      // columns per pass (batch rows or prefill toke
 constexpr int MAXSPLIT = 16;
 constexpr int RMAX = 2;          // max GQA group size (q heads per kv head)
 constexpr int PCOL = 20;         // padded row count of a partial column (bank-conflict-free)
-constexpr int XS_BYTES = 32 * (4096 + 64);  // staged activations: 32 cols x K=2048 bf16 (+64 B skew)
+constexpr int XS_COL_BYTES = 4096 + 64;     // one staged column: K=2048 bf16 (+64 B skew)
+constexpr int XS_BYTES = 32 * XS_COL_BYTES;  // staged activations at NT=4: 32 cols
+// Shared memory is sized per batch class (NT n8-tiles): a small request leaves most of the 228 KB as L1, which is
+// what absorbs register spills / ABI stack traffic (with a 216 KB request every spill is an L2 round trip).
+constexpr int ATT_SMEM = (32 * 2 * 128 + 32 * 2 * 130) * 4;   // attention: qs + per-half-warp partials
+constexpr int SAMPLER_SMEM = (2 * 4096 + 64 + 256) * 4;
+__host__ __device__ constexpr int xs_bytes_nt(int nt) { return nt * 8 * XS_COL_BYTES; }
+__host__ __device__ constexpr int part_bytes_nt(int nt) { return 16 * 2 * nt * 8 * 20 * 4; }
+__host__ __device__ constexpr int smem_bytes_nt(int nt) {
+  return (xs_bytes_nt(nt) + part_bytes_nt(nt) > ATT_SMEM ? xs_bytes_nt(nt) + part_bytes_nt(nt) : ATT_SMEM) + 1024;
+}
 constexpr int MAXV = 4096;       // max vocab handled by the sampler
 
 enum PhaseType { PH_GEMV = 0, PH_ATTN = 1, PH_SAMPLE = 2 };
@@ -60,6 +70,7 @@ struct Phase {
   // ---- GEMV
   const uint4* w;      // packed weights
   int n_tiles, kb;     // rows/16, K/32
+  int tq, tr;          // n_tiles = tq*grid + tr: CTA c owns tq (+1 if c < tr) consecutive tiles
   const bf16* src;     // [nc][src_ld]
   int src_ld;
   const bf16* norm_w;  // RMSNorm weight applied while staging (nullable)
@@ -115,6 +126,9 @@ struct KParams {
   DevState* st;
   StackDev talker, cp;
   int G, eos, has_proj;
+  int B;                    // sequences in this request (constant per launch)
+  int len0[MAXB];           // prompt lengths
+  int trailing_len[MAXB];
   q3_sampling sp;
   // sampler / embed resources
   const bf16* emb_t;        // talker codec_embedding [V][H]
@@ -133,6 +147,7 @@ struct KParams {
   int n_forced;
   float* dbg_tlogits;
   float* dbg_clogits;
+  unsigned long long* prof;  // [n_phases][8] globaltimer ns: [0] phase end, [1] barrier end, [2..5] inner marks (CTA 0)
   ChunkDesc chunk;
 };
 
@@ -140,50 +155,59 @@ struct KParams {
 // grid barrier (monotonic counter; arrive = release, wait = acquire)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void grid_barrier(DevState* st, unsigned int& epoch) {
-  __syncthreads();
+  __syncthreads();  // every thread's global writes happen-before thread 0's release (bar.sync is cumulative)
   if (threadIdx.x == 0) {
     epoch += gridDim.x;
-    __threadfence();
-    atomicAdd(&st->bar_count, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&st->bar_count) : "memory");
     long long t0 = clock64();
     unsigned int v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&st->bar_count));
-      if ((int)(v - epoch) < 0 && clock64() - t0 > 8000000000LL) {  // ~4 s: never hang the box
+    while (true) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&st->bar_count) : "memory");
+      if ((int)(v - epoch) >= 0) break;
+      if (clock64() - t0 > 8000000000LL) {  // ~4 s: never hang the box
         st->error = 77;
         __threadfence();
         __trap();
       }
-    } while ((int)(v - epoch) < 0);
-    __threadfence();
+    }
   }
-  __syncthreads();
+  __syncthreads();  // cross-CTA data is always read with ld.global.cg (L2), so no L1 invalidation is needed here
 }
+
+// fine-grained profiling marks (thread 0 of CTA 0 only, first frame of a profiled launch)
+__shared__ unsigned long long* g_prof_row;
+#define PROF_MARK(k)                                                                   \
+  do {                                                                                 \
+    if (threadIdx.x == 0 && g_prof_row) {                                              \
+      unsigned long long _t;                                                           \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                          \
+      g_prof_row[k] = _t;                                                              \
+    }                                                                                  \
+  } while (0)
+
+// NOTE ON CODE SIZE: the frame program walks ~560 phases per frame-step, alternating between the three phase
+// bodies below.  Their combined hot code must stay inside the SM's ~32 KB instruction cache, otherwise every
+// phase re-fetches its instructions from L2 (measured: ~4 us of pure fetch stall per phase with 150 KB of code).
+// Hence: loops are rolled (#pragma unroll 1) wherever latency is not at stake, bulk data goes through shared
+// memory instead of unrolled register arrays, and there is no 64-bit division on the device.
 
 // ------------------------------------------------------------------------------------------------
 // block-wide helpers (NTHREADS threads)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float block_max(float v, float* red) {
-  v = warp_max(v);
+__device__ __noinline__ float block_reduce(float v, float* red, int op /*0 max, 1 sum*/) {
+  if (op == 0) v = warp_max(v); else v = warp_sum(v);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   float r = red[threadIdx.x & (NWARPS - 1)];
 #pragma unroll
-  for (int o = NWARPS / 2; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+  for (int o = NWARPS / 2; o > 0; o >>= 1) {
+    const float n = __shfl_xor_sync(0xffffffffu, r, o);
+    r = op == 0 ? fmaxf(r, n) : r + n;
+  }
   return r;
 }
-__device__ __forceinline__ float block_sum(float v, float* red) {
-  v = warp_sum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  float r = red[threadIdx.x & (NWARPS - 1)];
-#pragma unroll
-  for (int o = NWARPS / 2; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-  return r;
-}
-__device__ __forceinline__ int block_min_int(int v, int* red) {
+__device__ __noinline__ int block_min_int(int v, int* red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
   __syncthreads();
@@ -194,140 +218,190 @@ __device__ __forceinline__ int block_min_int(int v, int* red) {
   for (int o = NWARPS / 2; o > 0; o >>= 1) r = min(r, __shfl_xor_sync(0xffffffffu, r, o));
   return r;
 }
-__device__ __forceinline__ int block_max_int(int v, int* red) { return -block_min_int(-v, red); }
 
 // ------------------------------------------------------------------------------------------------
 // GEMV phase:  dst[col][row] = epi( sum_k W[row][k] * x[col][k] )
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ int xs_stride_bytes(int K) { return ((K * 2 + 127) / 128) * 128 + 64; }
 
-__device__ __forceinline__ int phase_nc(const Phase& ph, const KParams& P) {
-  int B = P.st->B;
-  return ph.ncmode == NC_B ? B : (ph.ncmode == NC_2B ? 2 * B : P.chunk.nc);
+__device__ __forceinline__ int phase_nc(int ncmode, const KParams& P) {
+  const int B = P.B;
+  return ncmode == NC_B ? B : (ncmode == NC_2B ? 2 * B : P.chunk.nc);
 }
 
-__device__ void prefetch_phase_weights(const Phase& ph) {
+// balanced contiguous split of a phase's row tiles over the CTAs (tq/tr precomputed on the host)
+__device__ __forceinline__ void cta_tiles(int tq, int tr, int& t0, int& ntc) {
+  const int c = blockIdx.x;
+  t0 = c * tq + min(c, tr);
+  ntc = tq + (c < tr ? 1 : 0);
+}
+
+__device__ __forceinline__ void prefetch_phase_weights(const Phase& ph) {
   if (ph.type != PH_GEMV) return;
-  const int G = gridDim.x, c = blockIdx.x;
-  long long t0 = (long long)ph.n_tiles * c / G, t1 = (long long)ph.n_tiles * (c + 1) / G;
-  if (t1 <= t0) return;
-  const char* base = reinterpret_cast<const char*>(ph.w) + (size_t)t0 * ph.kb * 1024;
-  size_t bytes = (size_t)(t1 - t0) * ph.kb * 1024;
-  const size_t CH = 32768;
-  for (size_t off = (size_t)threadIdx.x * CH; off < bytes; off += (size_t)NTHREADS * CH) {
-    size_t n = bytes - off < CH ? bytes - off : CH;
-    l2_prefetch_bulk(base + off, (uint32_t)n);
+  int t0, ntc;
+  cta_tiles(ph.tq, ph.tr, t0, ntc);
+  const unsigned int bytes = (unsigned int)ntc * (unsigned int)ph.kb * 1024u;
+  const unsigned int off = threadIdx.x * 32768u;
+  if (off < bytes) {
+    const char* base = reinterpret_cast<const char*>(ph.w) + (size_t)t0 * ph.kb * 1024;
+    l2_prefetch_bulk(base + off, min(32768u, bytes - off));
+  }
+}
+
+// stage x (optionally RMS-normed) into smem as bf16 [col][K] (rows skewed by 64 B).  One warp per column; a lane
+// issues up to 8 independent 16-byte loads (K <= 2048 per pass) before touching the data; the RMSNorm runs on the
+// registers (sum of squares -> warp reduce -> scale) and the result is written to smem once.  The norm weights
+// were prefetched into nw_s one phase ahead (see the main loop), so they cost no global round trip here.
+__device__ __forceinline__ void stage_columns(const bf16* __restrict__ src, int src_ld, bool normed, float eps,
+                                              bf16* __restrict__ save, int K, int nc, char* __restrict__ xs, int xstride,
+                                              const uint4* __restrict__ nw_s) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nv = K >> 3;
+#pragma unroll 1
+  for (int col = warp; col < nc; col += NWARPS) {
+    const uint4* xr = reinterpret_cast<const uint4*>(src + (size_t)col * src_ld);
+    uint4* drow = reinterpret_cast<uint4*>(xs + (size_t)col * xstride);
+#pragma unroll 1
+    for (int vb = 0; vb < nv; vb += 256) {  // warp-uniform trip count (warp_sum below); one pass when K <= 2048
+      const int v0 = vb + lane;
+      uint4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (v0 + 32 * i < nv) v[i] = ldcg16(xr + v0 + 32 * i);
+      if (normed) {
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (v0 + 32 * i < nv) {
+            float f;
+            f = bf16lo(v[i].x); ss += f * f; f = bf16hi(v[i].x); ss += f * f;
+            f = bf16lo(v[i].y); ss += f * f; f = bf16hi(v[i].y); ss += f * f;
+            f = bf16lo(v[i].z); ss += f * f; f = bf16hi(v[i].z); ss += f * f;
+            f = bf16lo(v[i].w); ss += f * f; f = bf16hi(v[i].w); ss += f * f;
+          }
+        }
+        ss = warp_sum(ss);
+        const float inv = rsqrtf(ss / (float)K + eps);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (v0 + 32 * i < nv) {
+            const uint4 w = nw_s[v0 + 32 * i];
+            uint4 o;
+            o.x = pack_bf16(rbf(bf16lo(v[i].x) * inv) * bf16lo(w.x), rbf(bf16hi(v[i].x) * inv) * bf16hi(w.x));
+            o.y = pack_bf16(rbf(bf16lo(v[i].y) * inv) * bf16lo(w.y), rbf(bf16hi(v[i].y) * inv) * bf16hi(w.y));
+            o.z = pack_bf16(rbf(bf16lo(v[i].z) * inv) * bf16lo(w.z), rbf(bf16hi(v[i].z) * inv) * bf16hi(w.z));
+            o.w = pack_bf16(rbf(bf16lo(v[i].w) * inv) * bf16lo(w.w), rbf(bf16hi(v[i].w) * inv) * bf16hi(w.w));
+            v[i] = o;
+            if (save) reinterpret_cast<uint4*>(save + (size_t)col * K)[v0 + 32 * i] = o;
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (v0 + 32 * i < nv) drow[v0 + 32 * i] = v[i];
+    }
+  }
+}
+
+constexpr int DEPTH = 4;  // k32-blocks (2 x 16 B per lane each) kept in flight per warp
+
+__device__ __forceinline__ void gemv_preload(uint4 (&a)[DEPTH][2], const uint4* __restrict__ wp, int nk) {
+#pragma unroll
+  for (int i = 0; i < DEPTH; ++i)
+    if (i < nk) { a[i][0] = ldg_stream(wp + i * 64); a[i][1] = ldg_stream(wp + i * 64 + 32); }
+}
+
+template <int NT, bool STAGED>
+__device__ __forceinline__ void gemv_segment(float (&acc)[NT][4], uint4 (&a)[DEPTH][2], const uint4* __restrict__ wp, int nk, int kb0,
+                                             const char* __restrict__ xs, int xstride, const bf16* __restrict__ src,
+                                             int src_ld, int nc, int g, int t) {
+  // rolling register pipeline: DEPTH k32-blocks (2 x 16 B per lane each) always in flight; a slot is refilled the
+  // moment it has been copied out, so no fragment is ever held twice
+#pragma unroll 1
+  for (int k0 = 0; k0 < nk; k0 += DEPTH) {
+#pragma unroll
+    for (int i = 0; i < DEPTH; ++i) {
+      if (k0 + i < nk) {
+        const int kb = kb0 + k0 + i;
+        const uint4 r = a[i][0], s = a[i][1];
+        if (k0 + i + DEPTH < nk) {
+          a[i][0] = ldg_stream(wp + (k0 + i + DEPTH) * 64);
+          a[i][1] = ldg_stream(wp + (k0 + i + DEPTH) * 64 + 32);
+        }
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          uint4 b;
+          const int col = n * 8 + g;
+          if (STAGED) {
+            b = *reinterpret_cast<const uint4*>(xs + (size_t)col * xstride + kb * 64 + t * 16);
+          } else {
+            b = (col < nc) ? ldcg16(src + (size_t)col * src_ld + kb * 32 + t * 8) : make_uint4(0, 0, 0, 0);
+          }
+          mma_bf16_16816(acc[n], r.x, s.x, r.y, s.y, b.x, b.y);
+          mma_bf16_16816(acc[n], r.z, s.z, r.w, s.w, b.z, b.w);
+        }
+      }
+    }
   }
 }
 
 template <int NT>
-__device__ void gemv_phase(const Phase& ph, const KParams& P, unsigned char* smem) {
-  const int G = gridDim.x, c = blockIdx.x;
+__device__ __noinline__ void gemv_phase(const Phase& ph, const KParams& P, unsigned char* smem, const uint4* nw_s) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int nc = phase_nc(ph, P);
-  const int KB = ph.kb, K = KB * 32;
-  const int t0 = (int)((long long)ph.n_tiles * c / G), t1 = (int)((long long)ph.n_tiles * (c + 1) / G);
-  const int ntc = t1 - t0;
+  // descriptor fields -> registers once
+  const uint4* const wbase = ph.w;
+  const int KB = ph.kb, K = KB * 32, epi = ph.epi;
+  const bf16* const src = ph.src;
+  const int src_ld = ph.src_ld, dst_ld = ph.dst_ld;
+  const bf16* const norm_w = ph.norm_w;
+  void* const dst = ph.dst;
+  const bf16* const bias = ph.bias;
+  const int nc = phase_nc(ph.ncmode, P);
+  int t0, ntc;
+  cta_tiles(ph.tq, ph.tr, t0, ntc);
 
-  bf16* xs = reinterpret_cast<bf16*>(smem);
-  float* part = reinterpret_cast<float*>(smem + XS_BYTES);  // [NWARPS][2][NT*8][PCOL]
+  char* xs = reinterpret_cast<char*>(smem);
+  float* part = reinterpret_cast<float*>(smem + xs_bytes_nt(NT));  // [NWARPS][2][NT*8][PCOL]
   const int xstride = xs_stride_bytes(K);
-  const bool staged = (ph.norm_w != nullptr) || ((size_t)xstride * (NT * 8) <= (size_t)XS_BYTES);
-  const bool need_stage = staged && (ntc > 0 || (ph.save_normed != nullptr && c == 0));
-
-  // ---- prologue: stage x (optionally RMS-normed) into smem as bf16 [col][K] (skewed rows)
-  if (need_stage) {
-    for (int col = warp; col < nc; col += NWARPS) {
-      const bf16* xr = ph.src + (size_t)col * ph.src_ld;
-      char* drow = reinterpret_cast<char*>(xs) + (size_t)col * xstride;
-      if (ph.norm_w) {
-        float ss = 0.f;
-        for (int k = lane * 8; k < K; k += 256) {
-          uint4 v = ldcg16(xr + k);
-          float f;
-          f = bf16lo(v.x); ss += f * f; f = bf16hi(v.x); ss += f * f;
-          f = bf16lo(v.y); ss += f * f; f = bf16hi(v.y); ss += f * f;
-          f = bf16lo(v.z); ss += f * f; f = bf16hi(v.z); ss += f * f;
-          f = bf16lo(v.w); ss += f * f; f = bf16hi(v.w); ss += f * f;
-        }
-        ss = warp_sum(ss);
-        const float inv = rsqrtf(ss / (float)K + ph.eps);
-        for (int k = lane * 8; k < K; k += 256) {
-          uint4 v = ldcg16(xr + k);
-          uint4 w = *reinterpret_cast<const uint4*>(ph.norm_w + k);
-          uint4 o;
-          o.x = pack_bf16(rbf(bf16lo(v.x) * inv) * bf16lo(w.x), rbf(bf16hi(v.x) * inv) * bf16hi(w.x));
-          o.y = pack_bf16(rbf(bf16lo(v.y) * inv) * bf16lo(w.y), rbf(bf16hi(v.y) * inv) * bf16hi(w.y));
-          o.z = pack_bf16(rbf(bf16lo(v.z) * inv) * bf16lo(w.z), rbf(bf16hi(v.z) * inv) * bf16hi(w.z));
-          o.w = pack_bf16(rbf(bf16lo(v.w) * inv) * bf16lo(w.w), rbf(bf16hi(v.w) * inv) * bf16hi(w.w));
-          *reinterpret_cast<uint4*>(drow + k * 2) = o;
-          if (ph.save_normed && c == 0) *reinterpret_cast<uint4*>(ph.save_normed + (size_t)col * K + k) = o;
-        }
-      } else {
-        for (int k = lane * 8; k < K; k += 256)
-          *reinterpret_cast<uint4*>(drow + k * 2) = ldcg16(xr + k);
-      }
-    }
+  const bool staged = (norm_w != nullptr) || (xstride * (NT * 8) <= xs_bytes_nt(NT));
+  bf16* const save = (ph.save_normed != nullptr && blockIdx.x == 0) ? ph.save_normed : nullptr;
+  // first weight fragments of this warp go in flight BEFORE the activations are staged (they do not depend on x)
+  uint4 afr[DEPTH][2];
+  const int TB0 = min(NWARPS, ntc);
+  const int upw0 = (TB0 * KB + NWARPS - 1) / NWARPS;
+  const bool have0 = ntc > 0 && warp * upw0 < TB0 * KB;
+  if (have0) {
+    const int u = warp * upw0, tl = u / KB, kb0 = u - tl * KB;
+    gemv_preload(afr, wbase + ((size_t)(t0 + tl) * KB + kb0) * 64 + lane, min(KB - kb0, min(TB0 * KB, u + upw0) - u));
   }
+  PROF_MARK(2);
+  if (staged && (ntc > 0 || save)) stage_columns(src, src_ld, norm_w != nullptr, ph.eps, save, K, nc, xs, xstride, nw_s);
   __syncthreads();
+  PROF_MARK(3);
   if (ntc <= 0) return;
 
-  // ---- main loop over batches of <= NWARPS row tiles
+#pragma unroll 1
   for (int tb0 = 0; tb0 < ntc; tb0 += NWARPS) {
     const int TB = min(NWARPS, ntc - tb0);
     const int units = TB * KB;
     const int upw = (units + NWARPS - 1) / NWARPS;
-    const int u0 = warp * upw, u1 = min(units, u0 + upw);
+    const int u1 = min(units, (warp + 1) * upw);
     int seg = 0;
-    int u = u0;
-    while (u < u1) {
+#pragma unroll 1
+    for (int u = warp * upw; u < u1;) {
       const int tl = u / KB;
       const int kb0 = u - tl * KB;
-      const int kb1 = min(KB, kb0 + (u1 - u));
+      const int nk = min(KB - kb0, u1 - u);
       float acc[NT][4];
 #pragma unroll
       for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-      const uint4* wp = ph.w + ((size_t)(t0 + tb0 + tl) * KB + kb0) * 64 + lane;
-      const int nk = kb1 - kb0;
-      // software pipeline: groups of 4 k32-blocks, next group in flight while this one is consumed
-      uint4 a_cur[4][2], a_nxt[4][2];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (i < nk) { a_cur[i][0] = ldg_stream(wp + i * 64); a_cur[i][1] = ldg_stream(wp + i * 64 + 32); }
-      for (int k0 = 0; k0 < nk; k0 += 4) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (k0 + 4 + i < nk) {
-            a_nxt[i][0] = ldg_stream(wp + (k0 + 4 + i) * 64);
-            a_nxt[i][1] = ldg_stream(wp + (k0 + 4 + i) * 64 + 32);
-          }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (k0 + i < nk) {
-            const int kb = kb0 + k0 + i;
-            const uint4 r = a_cur[i][0], s = a_cur[i][1];
-#pragma unroll
-            for (int n = 0; n < NT; ++n) {
-              uint4 b;
-              const int col = n * 8 + g;
-              if (staged) {
-                b = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(xs) + (size_t)col * xstride +
-                                                    kb * 64 + t * 16);
-              } else {
-                if (col < nc) b = ldcg16(ph.src + (size_t)col * ph.src_ld + kb * 32 + t * 8);
-                else b = make_uint4(0, 0, 0, 0);
-              }
-              mma_bf16_16816(acc[n], r.x, s.x, r.y, s.y, b.x, b.y);
-              mma_bf16_16816(acc[n], r.z, s.z, r.w, s.w, b.z, b.w);
-            }
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { a_cur[i][0] = a_nxt[i][0]; a_cur[i][1] = a_nxt[i][1]; }
-      }
+      const uint4* wp = wbase + ((size_t)(t0 + tb0 + tl) * KB + kb0) * 64 + lane;
+      if (!(tb0 == 0 && seg == 0)) gemv_preload(afr, wp, nk);  // the very first segment was preloaded above
+      if (staged) gemv_segment<NT, true>(acc, afr, wp, nk, kb0, xs, xstride, src, src_ld, nc, g, t);
+      else gemv_segment<NT, false>(acc, afr, wp, nk, kb0, xs, xstride, src, src_ld, nc, g, t);
       // spill partial sums: part[warp][seg][col][row]
-      float* pp = part + ((size_t)(warp * 2 + seg) * (NT * 8)) * PCOL;
+      float* pp = part + ((warp * 2 + seg) * (NT * 8)) * PCOL;
 #pragma unroll
       for (int n = 0; n < NT; ++n) {
         const int col = n * 8 + 2 * t;
@@ -340,42 +414,44 @@ __device__ void gemv_phase(const Phase& ph, const KParams& P, unsigned char* sme
       u += nk;
     }
     __syncthreads();
-    // ---- cross-warp reduce + epilogue
-    const int rows_per_tile = (ph.epi == EPI_SWIGLU) ? 8 : 16;
-    const int nelem = TB * rows_per_tile * nc;
+    PROF_MARK(4);
+    // ---- cross-warp reduce + epilogue, one element per thread-iteration (independent global round trips)
+    const bool swiglu = epi == EPI_SWIGLU;
+    const int rsh = swiglu ? 3 : 4;  // rows per tile: 8 (gate/up pairs) or 16
+    const int nelem = (TB << rsh) * nc;
+#pragma unroll 1
     for (int e = tid; e < nelem; e += NTHREADS) {
-      const int r = e % rows_per_tile;
-      const int tl = (e / rows_per_tile) % TB;
-      const int col = e / (rows_per_tile * TB);
+      const int r = e & ((1 << rsh) - 1);
+      const int q = e >> rsh;
+      const int col = q / TB, tl = q - col * TB;
       const int wf = (tl * KB) / upw, wl = ((tl + 1) * KB - 1) / upw;
+      const int tile = t0 + tb0 + tl;
+      const int row = tile * 16 + r;
+      float resid = 0.f;
+      if (epi == EPI_RESID) resid = bf2f(ldcg_bf16(reinterpret_cast<bf16*>(dst) + (size_t)col * dst_ld + row));  // in flight
       float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
       for (int w = wf; w <= wl; ++w) {
         const int sg = tl - (w * upw) / KB;
-        const float* pp = part + ((size_t)(w * 2 + sg) * (NT * 8) + col) * PCOL;
+        const float* pp = part + ((w * 2 + sg) * (NT * 8) + col) * PCOL;
         s0 += pp[r];
-        if (ph.epi == EPI_SWIGLU) s1 += pp[r + 8];
+        if (swiglu) s1 += pp[r + 8];
       }
-      const int tile = t0 + tb0 + tl;
-      if (ph.epi == EPI_SWIGLU) {
+      if (swiglu) {
         // rows 0-7 = gate, 8-15 = up of the same 8 intermediate channels (:853-855, bf16 rounding points)
         const float gt = rbf(s0), up = rbf(s1);
         const float sl = rbf(gt / (1.f + __expf(-gt)));
-        reinterpret_cast<bf16*>(ph.dst)[(size_t)col * ph.dst_ld + tile * 8 + r] = f2bf(sl * up);
+        reinterpret_cast<bf16*>(dst)[(size_t)col * dst_ld + tile * 8 + r] = f2bf(sl * up);
+      } else if (epi == EPI_LOGITS) {  // bf16 linear output, then .float() (HF _sample)
+        reinterpret_cast<float*>(dst)[(size_t)col * dst_ld + row] = rbf(s0);
       } else {
-        const int row = tile * 16 + r;
-        if (ph.epi == EPI_STORE) {
-          reinterpret_cast<bf16*>(ph.dst)[(size_t)col * ph.dst_ld + row] = f2bf(s0);
-        } else if (ph.epi == EPI_BIAS) {
-          reinterpret_cast<bf16*>(ph.dst)[(size_t)col * ph.dst_ld + row] = f2bf(s0 + bf2f(ph.bias[row]));
-        } else if (ph.epi == EPI_RESID) {
-          bf16* d = reinterpret_cast<bf16*>(ph.dst) + (size_t)col * ph.dst_ld + row;
-          *d = f2bf(bf2f(ldcg_bf16(d)) + rbf(s0));
-        } else {  // EPI_LOGITS: bf16 linear output, then .float() (HF _sample)
-          reinterpret_cast<float*>(ph.dst)[(size_t)col * ph.dst_ld + row] = rbf(s0);
-        }
+        if (epi == EPI_BIAS) s0 += bf2f(bias[row]);
+        else if (epi == EPI_RESID) s0 = resid + rbf(s0);
+        reinterpret_cast<bf16*>(dst)[(size_t)col * dst_ld + row] = f2bf(s0);
       }
     }
     __syncthreads();
+    PROF_MARK(5);
   }
 }
 
@@ -383,86 +459,93 @@ __device__ void gemv_phase(const Phase& ph, const KParams& P, unsigned char* sme
 // attention phase (per (sequence, kv head, split) unit): q/k RMSNorm + RoPE, KV append, single-query GQA
 // ------------------------------------------------------------------------------------------------
 // one warp normalises + rotates one 128-vector; lane owns dims {l, l+32, l+64, l+96}
-__device__ __forceinline__ void norm_rope_vec(const bf16* src, const bf16* nw, float eps, const bf16* cosr,
-                                              const bf16* sinr, float (&out)[4]) {
+__device__ __noinline__ void norm_rope_vec(const bf16* src, const bf16* nw, float eps, const bf16* cosr, const bf16* sinr,
+                                           float* out_f32, bf16* out_bf16) {
   const int lane = threadIdx.x & 31;
-  float x[4];
+  float x[4], w[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) x[i] = bf2f(ldcg_bf16(src + lane + 32 * i));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w[i] = bf2f(nw[lane + 32 * i]);
+  // rotate_half pairs: (l, l+64) and (l+32, l+96); cos/sin tables are [64] (emb = cat(freqs, freqs))
+  const float c0 = bf2f(cosr[lane]), s0 = bf2f(sinr[lane]);
+  const float c1 = bf2f(cosr[lane + 32]), s1 = bf2f(sinr[lane + 32]);
   float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
   ss = warp_sum(ss);
   const float inv = rsqrtf(ss / (float)HD + eps);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) x[i] = rbf(rbf(x[i] * inv) * bf2f(nw[lane + 32 * i]));
-  // rotate_half pairs: (l, l+64) and (l+32, l+96); cos/sin tables are [64] (emb = cat(freqs, freqs))
-  const float c0 = bf2f(cosr[lane]), s0 = bf2f(sinr[lane]);
-  const float c1 = bf2f(cosr[lane + 32]), s1 = bf2f(sinr[lane + 32]);
-  out[0] = rbf(rbf(x[0] * c0) + rbf(-x[2] * s0));
-  out[2] = rbf(rbf(x[2] * c0) + rbf(x[0] * s0));
-  out[1] = rbf(rbf(x[1] * c1) + rbf(-x[3] * s1));
-  out[3] = rbf(rbf(x[3] * c1) + rbf(x[1] * s1));
+  for (int i = 0; i < 4; ++i) x[i] = rbf(rbf(x[i] * inv) * w[i]);
+  float o[4];
+  o[0] = rbf(rbf(x[0] * c0) + rbf(-x[2] * s0));
+  o[2] = rbf(rbf(x[2] * c0) + rbf(x[0] * s0));
+  o[1] = rbf(rbf(x[1] * c1) + rbf(-x[3] * s1));
+  o[3] = rbf(rbf(x[3] * c1) + rbf(x[1] * s1));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (out_f32) out_f32[lane + 32 * i] = o[i];
+    else out_bf16[lane + 32 * i] = f2bf(o[i]);
+  }
 }
 
-__device__ void attn_phase(const Phase& ph, const KParams& P, unsigned char* smem, int frame) {
+__device__ __noinline__ void attn_phase(const Phase& ph, const KParams& P, unsigned char* smem, int frame) {
   const StackDev& S = ph.stack == 0 ? P.talker : P.cp;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int R = S.nh / S.nkv;  // <= RMAX
-  const int B = P.st->B;
-  const int qkv_ld = (S.nh + 2 * S.nkv) * HD;
-  const int nseq = ph.seqmode == SEQ_PREFILL ? P.chunk.nseq : B;
+  const int nh = S.nh, nkv = S.nkv, layers = S.layers, cap = S.cap;
+  const int R = nh / nkv;  // <= RMAX
+  const int B = P.B;
+  const int qkv_ld = (nh + 2 * nkv) * HD;
+  const int seqmode = ph.seqmode, layer = ph.layer;
+  const int nseq = seqmode == SEQ_PREFILL ? P.chunk.nseq : B;
+  const float eps = S.eps;
+  const bf16 *qn = ph.qn, *kn = ph.kn;
 
   int nsplit = 1;
-  if (ph.seqmode == SEQ_DECODE) {
+  if (seqmode == SEQ_DECODE) {
     int cmax = 0;
-    for (int b = 0; b < B; ++b) cmax = max(cmax, P.st->len0[b] + frame + 1);
-    int byctx = (cmax + 127) / 128;
-    int bygrid = (int)gridDim.x / (B * S.nkv);
+    for (int b = 0; b < B; ++b) cmax = max(cmax, P.len0[b]);
+    cmax += frame + 1;
+    const int byctx = (cmax + 127) >> 7;
+    const int bygrid = (int)gridDim.x / (B * nkv);
     nsplit = max(1, min(min(byctx, bygrid), MAXSPLIT));
   }
-  const int units = nseq * S.nkv * nsplit;
+  const int units = nseq * nkv * nsplit;
 
   float* qs = reinterpret_cast<float*>(smem);                 // [nq<=32][RMAX][128]
   float* red = qs + 32 * RMAX * HD;                           // [32 halfwarps][RMAX][130]
   __shared__ int s_ticket;
 
+#pragma unroll 1
   for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
     const int sp = unit % nsplit;
-    const int kvh = (unit / nsplit) % S.nkv;
-    const int si = unit / (nsplit * S.nkv);
+    const int kvh = (unit / nsplit) % nkv;
+    const int si = unit / (nsplit * nkv);
     int seq, q0, nq, qstride, ctx_end;
-    if (ph.seqmode == SEQ_CP) { seq = si; q0 = si; nq = ph.nq; qstride = B; ctx_end = ph.ctx_end; }
-    else if (ph.seqmode == SEQ_DECODE) { seq = si; q0 = si; nq = 1; qstride = 0; ctx_end = P.st->len0[si] + frame + 1; }
+    if (seqmode == SEQ_CP) { seq = si; q0 = si; nq = ph.nq; qstride = B; ctx_end = ph.ctx_end; }
+    else if (seqmode == SEQ_DECODE) { seq = si; q0 = si; nq = 1; qstride = 0; ctx_end = P.len0[si] + frame + 1; }
     else { seq = P.chunk.seq_id[si]; q0 = P.chunk.q0[si]; nq = P.chunk.nq[si]; qstride = 1; ctx_end = P.chunk.ctx_end[si]; }
     const int SL = (ctx_end + nsplit - 1) / nsplit;
     const int s0 = sp * SL, s1 = min(ctx_end, s0 + SL);
-    bf16* kc = S.kc + (((size_t)seq * S.layers + ph.layer) * S.nkv + kvh) * (size_t)S.cap * HD;
-    bf16* vc = S.vc + (((size_t)seq * S.layers + ph.layer) * S.nkv + kvh) * (size_t)S.cap * HD;
+    bf16* kc = S.kc + (((size_t)seq * layers + layer) * nkv + kvh) * (size_t)cap * HD;
+    bf16* vc = S.vc + (((size_t)seq * layers + layer) * nkv + kvh) * (size_t)cap * HD;
 
-    // ---- step A/B: per query token: q heads -> smem (fp32), k (norm+rope) and v -> cache (owner split only)
+    // ---- per query token: q heads -> smem (fp32), k (norm+rope) and v -> cache (owner split only)
     const int nvec = nq * (R + 2);
+#pragma unroll 1
     for (int v = warp; v < nvec; v += NWARPS) {
-      const int j = v / (R + 2), which = v % (R + 2);
+      const int j = v / (R + 2), which = v - j * (R + 2);
       const int col = q0 + j * qstride;
       const int pos = ctx_end - nq + j;
       const bool owner = (pos >= s0 && pos < s1);
       const bf16* base = S.qkv + (size_t)col * qkv_ld;
+      const bf16* cosr = S.rope_cos + (size_t)pos * 64;
+      const bf16* sinr = S.rope_sin + (size_t)pos * 64;
       if (which < R) {
-        float o[4];
-        norm_rope_vec(base + (kvh * R + which) * HD, ph.qn, S.eps, S.rope_cos + (size_t)pos * 64,
-                      S.rope_sin + (size_t)pos * 64, o);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) qs[(j * RMAX + which) * HD + lane + 32 * i] = o[i];
-      } else if (which == R) {
-        if (owner) {
-          float o[4];
-          norm_rope_vec(base + (S.nh + kvh) * HD, ph.kn, S.eps, S.rope_cos + (size_t)pos * 64,
-                        S.rope_sin + (size_t)pos * 64, o);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) kc[(size_t)pos * HD + lane + 32 * i] = f2bf(o[i]);
-        }
-      } else {
-        if (owner) {
-          const bf16* vsrc = base + (S.nh + S.nkv + kvh) * HD;
+        norm_rope_vec(base + (kvh * R + which) * HD, qn, eps, cosr, sinr, qs + (j * RMAX + which) * HD, nullptr);
+      } else if (owner) {
+        if (which == R) {
+          norm_rope_vec(base + (nh + kvh) * HD, kn, eps, cosr, sinr, nullptr, kc + (size_t)pos * HD);
+        } else {
+          const bf16* vsrc = base + (nh + nkv + kvh) * HD;
 #pragma unroll
           for (int i = 0; i < 4; ++i) vc[(size_t)pos * HD + lane + 32 * i] = ldcg_bf16(vsrc + lane + 32 * i);
         }
@@ -470,9 +553,12 @@ __device__ void attn_phase(const Phase& ph, const KParams& P, unsigned char* sme
     }
     __threadfence_block();
     __syncthreads();
+    PROF_MARK(2);
 
     const float scale = rsqrtf((float)HD);
     const int hw = warp * 2 + (lane >> 4), l16 = lane & 15;
+    const int rr_ = tid >> 7, dd = tid & (HD - 1);
+#pragma unroll 1
     for (int j = 0; j < nq; ++j) {
       const int col = q0 + j * qstride;
       const int pos = ctx_end - nq + j;
@@ -489,42 +575,49 @@ __device__ void attn_phase(const Phase& ph, const KParams& P, unsigned char* sme
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[r][i] = 0.f;
       }
-      for (int tb = s0 + warp * 2; tb < e1; tb += 32) {  // warp-uniform trip count (full-mask shuffles below)
-        const int tk = tb + (lane >> 4);
-        const bool valid = tk < e1;
-        uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-        if (valid) {
-          kv = ldcg16(kc + (size_t)tk * HD + l16 * 8);
-          vv = ldcg16(vc + (size_t)tk * HD + l16 * 8);
-        }
-        float kf[8] = {bf16lo(kv.x), bf16hi(kv.x), bf16lo(kv.y), bf16hi(kv.y),
-                       bf16lo(kv.z), bf16hi(kv.z), bf16lo(kv.w), bf16hi(kv.w)};
-        float vf[8] = {bf16lo(vv.x), bf16hi(vv.x), bf16lo(vv.y), bf16hi(vv.y),
-                       bf16lo(vv.z), bf16hi(vv.z), bf16lo(vv.w), bf16hi(vv.w)};
+      // warp-uniform trip count (full-mask shuffles below); each half-warp handles 2 tokens per iteration so
+      // that 4 independent 16-byte loads are in flight before the dependent softmax update
+#pragma unroll 1
+      for (int tb = s0 + warp * 4; tb < e1; tb += 64) {
+        const int tk0 = tb + (lane >> 4), tk1 = tk0 + 2;
+        uint4 kv[2], vv[2];
+        kv[0] = kv[1] = vv[0] = vv[1] = make_uint4(0, 0, 0, 0);
+        if (tk0 < e1) { kv[0] = ldcg16(kc + (size_t)tk0 * HD + l16 * 8); vv[0] = ldcg16(vc + (size_t)tk0 * HD + l16 * 8); }
+        if (tk1 < e1) { kv[1] = ldcg16(kc + (size_t)tk1 * HD + l16 * 8); vv[1] = ldcg16(vc + (size_t)tk1 * HD + l16 * 8); }
 #pragma unroll
-        for (int r = 0; r < RMAX; ++r) {
-          if (r < R) {
-            float d = 0.f;
+        for (int u = 0; u < 2; ++u) {  // fully unrolled: register arrays must keep compile-time indices (no local memory)
+          const bool valid = (u == 0 ? tk0 : tk1) < e1;
+          const uint4 kk = kv[u], v4 = vv[u];
+          const float kf[8] = {bf16lo(kk.x), bf16hi(kk.x), bf16lo(kk.y), bf16hi(kk.y),
+                               bf16lo(kk.z), bf16hi(kk.z), bf16lo(kk.w), bf16hi(kk.w)};
+          const float vf[8] = {bf16lo(v4.x), bf16hi(v4.x), bf16lo(v4.y), bf16hi(v4.y),
+                               bf16lo(v4.z), bf16hi(v4.z), bf16lo(v4.w), bf16hi(v4.w)};
 #pragma unroll
-            for (int i = 0; i < 8; ++i) d += q[r][i] * kf[i];
-            d += __shfl_xor_sync(0xffffffffu, d, 8);
-            d += __shfl_xor_sync(0xffffffffu, d, 4);
-            d += __shfl_xor_sync(0xffffffffu, d, 2);
-            d += __shfl_xor_sync(0xffffffffu, d, 1);
-            if (valid) {
-              d *= scale;
-              const float mn = fmaxf(m[r], d);
-              const float corr = __expf(m[r] - mn);  // exp(-inf)=0 on the first token
-              const float p = __expf(d - mn);
-              l[r] = l[r] * corr + p;
+          for (int r = 0; r < RMAX; ++r) {
+            if (r < R) {
+              float d = 0.f;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) o[r][i] = o[r][i] * corr + p * vf[i];
-              m[r] = mn;
+              for (int i = 0; i < 8; ++i) d += q[r][i] * kf[i];
+              d += __shfl_xor_sync(0xffffffffu, d, 8);
+              d += __shfl_xor_sync(0xffffffffu, d, 4);
+              d += __shfl_xor_sync(0xffffffffu, d, 2);
+              d += __shfl_xor_sync(0xffffffffu, d, 1);
+              if (valid) {
+                d *= scale;
+                const float mn = fmaxf(m[r], d);
+                const float corr = __expf(m[r] - mn);  // exp(-inf)=0 on the first token
+                const float p = __expf(d - mn);
+                l[r] = l[r] * corr + p;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[r][i] = o[r][i] * corr + p * vf[i];
+                m[r] = mn;
+              }
             }
           }
         }
       }
       // ---- combine the 32 half-warps
+      PROF_MARK(3);
       __syncthreads();
 #pragma unroll
       for (int r = 0; r < RMAX; ++r) {
@@ -537,35 +630,43 @@ __device__ void attn_phase(const Phase& ph, const KParams& P, unsigned char* sme
       }
       __syncthreads();
       float M = -INFINITY, L = 0.f, O = 0.f;
-      const int rr_ = tid / HD, dd = tid % HD;
+      // token t of this split maps to half-warp ((t>>2)<<1) | (t&1): only the first nhw half-warps hold data
+      const int ntok = max(e1 - s0, 0);
+      const int nhw = min(32, ((ntok + 3) >> 2) << 1);
       if (rr_ < R) {
-        for (int h2 = 0; h2 < 32; ++h2) M = fmaxf(M, red[((size_t)h2 * RMAX + rr_) * 130]);
-        for (int h2 = 0; h2 < 32; ++h2) {
+#pragma unroll 2
+        for (int h2 = 0; h2 < nhw; ++h2) M = fmaxf(M, red[((size_t)h2 * RMAX + rr_) * 130]);
+#pragma unroll 2
+        for (int h2 = 0; h2 < nhw; ++h2) {
           const float* rp = red + ((size_t)h2 * RMAX + rr_) * 130;
           const float wgt = (rp[0] == -INFINITY) ? 0.f : __expf(rp[0] - M);
           L += rp[1] * wgt;
           O += rp[2 + dd] * wgt;
         }
       }
+      PROF_MARK(4);
+      bf16* outp = S.attn + (size_t)col * (nh * HD) + (kvh * R + rr_) * HD + dd;
       if (nsplit == 1) {
-        if (rr_ < R) S.attn[(size_t)col * (S.nh * HD) + (kvh * R + rr_) * HD + dd] = f2bf(O / L);
+        if (rr_ < R) *outp = f2bf(O / L);
       } else {
         // cross-CTA split combine: publish (M,L,O) and let the last arriver finish (deterministic order)
-        float* sb = P.split_buf + (((size_t)(seq * S.nkv + kvh) * MAXSPLIT + sp) * RMAX) * 130;
+        float* sb0 = P.split_buf + (((size_t)(seq * nkv + kvh) * MAXSPLIT) * RMAX) * 130;
+        float* sb = sb0 + ((size_t)sp * RMAX) * 130;
         if (rr_ < R) {
           if (dd == 0) { sb[rr_ * 130] = M; sb[rr_ * 130 + 1] = L; }
           sb[rr_ * 130 + 2 + dd] = O;
         }
         __threadfence();
         __syncthreads();
-        if (tid == 0) s_ticket = (int)atomicAdd(&P.st->split_cnt[seq * S.nkv + kvh], 1u);
+        if (tid == 0) s_ticket = (int)atomicAdd(&P.st->split_cnt[seq * nkv + kvh], 1u);
         __syncthreads();
         if (s_ticket == nsplit - 1) {
           __threadfence();
           if (rr_ < R) {
-            const float* sb0 = P.split_buf + (((size_t)(seq * S.nkv + kvh) * MAXSPLIT) * RMAX) * 130;
             float M2 = -INFINITY, L2 = 0.f, O2 = 0.f;
+#pragma unroll 1
             for (int s2 = 0; s2 < nsplit; ++s2) M2 = fmaxf(M2, ldcgf(sb0 + ((size_t)s2 * RMAX + rr_) * 130));
+#pragma unroll 1
             for (int s2 = 0; s2 < nsplit; ++s2) {
               const float* rp = sb0 + ((size_t)s2 * RMAX + rr_) * 130;
               const float mm = ldcgf(rp);
@@ -573,9 +674,9 @@ __device__ void attn_phase(const Phase& ph, const KParams& P, unsigned char* sme
               L2 += ldcgf(rp + 1) * wgt;
               O2 += ldcgf(rp + 2 + dd) * wgt;
             }
-            S.attn[(size_t)col * (S.nh * HD) + (kvh * R + rr_) * HD + dd] = f2bf(O2 / L2);
+            *outp = f2bf(O2 / L2);
           }
-          if (tid == 0) P.st->split_cnt[seq * S.nkv + kvh] = 0;
+          if (tid == 0) P.st->split_cnt[seq * nkv + kvh] = 0;
         }
       }
       __syncthreads();
@@ -592,12 +693,14 @@ __device__ __forceinline__ unsigned int fkey(float f) {
 }
 
 // k-th largest of sv[0..V) (block-wide radix select over 4x8 bits); returns the threshold value
-__device__ float kth_largest(const float* sv, int V, int k, unsigned int* hist, int* sh) {
+__device__ __noinline__ float kth_largest(const float* sv, int V, int k, unsigned int* hist, int* sh) {
   unsigned int prefix = 0, mask = 0;
+#pragma unroll 1
   for (int pass = 3; pass >= 0; --pass) {
     const int shift = pass * 8;
     if (threadIdx.x < 256) hist[threadIdx.x] = 0;
     __syncthreads();
+#pragma unroll 1
     for (int i = threadIdx.x; i < V; i += NTHREADS) {
       const unsigned int key = fkey(sv[i]);
       if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
@@ -619,6 +722,7 @@ __device__ float kth_largest(const float* sv, int V, int k, unsigned int* hist, 
     __syncthreads();
     if (threadIdx.x < 256) {
       unsigned int above = 0;
+#pragma unroll 1
       for (int w = (threadIdx.x >> 5) + 1; w < 8; ++w) above += (unsigned int)sh[w];
       incl += above;                       // elements with digit >= d
       const unsigned int excl = incl - cnt;  // elements with digit > d
@@ -634,12 +738,14 @@ __device__ float kth_largest(const float* sv, int V, int k, unsigned int* hist, 
   return __uint_as_float(u);
 }
 
-__device__ void sample_phase(const Phase& ph, const KParams& P, unsigned char* smem, int frame, bool in_prefill) {
+__device__ __noinline__ void sample_phase(const Phase& ph, const KParams& P, unsigned char* smem, int frame, bool in_prefill) {
   const int b = blockIdx.x;
   DevState* st = P.st;
-  if (b >= st->B) return;
+  const int B = P.B;
+  if (b >= B) return;
   const int tid = threadIdx.x;
-  const bool talker = ph.group == 0;
+  const int group = ph.group;
+  const bool talker = group == 0;
   const StackDev& S = talker ? P.talker : P.cp;
   const int V = S.vocab;
   const int H = P.talker.hidden;
@@ -655,22 +761,33 @@ __device__ void sample_phase(const Phase& ph, const KParams& P, unsigned char* s
   const int top_k = talker ? P.sp.top_k : P.sp.subtalker_top_k;
   const float top_p = talker ? P.sp.top_p : P.sp.subtalker_top_p;
   const float* lg = S.logits + (size_t)b * V;
+  const int n_gen_b = talker ? ldcgi(&st->n_gen[b]) : 0;
 
+  // raw logits -> smem with all loads of a thread in flight, then a rolled processing pass
+  {
+    float lreg[MAXV / NTHREADS];
+#pragma unroll
+    for (int r = 0; r < MAXV / NTHREADS; ++r) { const int i = tid + r * NTHREADS; if (i < V) lreg[r] = ldcgf(lg + i); }
+#pragma unroll
+    for (int r = 0; r < MAXV / NTHREADS; ++r) { const int i = tid + r * NTHREADS; if (i < V) sv[i] = lreg[r]; }
+  }
+  float* dbg = talker ? (P.dbg_tlogits ? P.dbg_tlogits + ((size_t)fidx * B + b) * V : nullptr)
+                      : (P.dbg_clogits ? P.dbg_clogits + (((size_t)frame * (P.G - 1) + (group - 1)) * B + b) * V : nullptr);
+  const float rp = P.sp.repetition_penalty;
+  const float inv_t = (do_sample && temperature != 1.0f) ? temperature : 1.0f;
+#pragma unroll 1
   for (int i = tid; i < V; i += NTHREADS) {
-    float s = ldcgf(lg + i);
+    float s = sv[i];
+    if (dbg) dbg[i] = s;
     if (talker) {
-      if (P.dbg_tlogits) P.dbg_tlogits[((size_t)fidx * st->B + b) * V + i] = s;
       // 1. repetition penalty over generated codebook-0 tokens
-      if (P.sp.repetition_penalty != 1.0f && __ldcg(P.seen + (size_t)b * V + i))
-        s = s < 0.f ? s * P.sp.repetition_penalty : s / P.sp.repetition_penalty;
+      if (rp != 1.0f && __ldcg(P.seen + (size_t)b * V + i)) s = s < 0.f ? s * rp : s / rp;
       // 2. min_new_tokens (and the fixed-horizon benchmark switch)
-      if (i == P.eos && (ldcgi(&st->n_gen[b]) < P.sp.min_new_tokens || P.sp.suppress_eos)) s = -INFINITY;
+      if (i == P.eos && (n_gen_b < P.sp.min_new_tokens || P.sp.suppress_eos)) s = -INFINITY;
       // 3. suppress [V-1024, V) \ {eos}
       if (i >= V - 1024 && i != P.eos) s = -INFINITY;
-    } else if (P.dbg_clogits) {
-      P.dbg_clogits[(((size_t)frame * (P.G - 1) + (ph.group - 1)) * st->B + b) * V + i] = s;
     }
-    if (do_sample && temperature != 1.0f) s = s / temperature;
+    if (inv_t != 1.0f) s = s / inv_t;
     sv[i] = s;
   }
   __syncthreads();
@@ -678,36 +795,43 @@ __device__ void sample_phase(const Phase& ph, const KParams& P, unsigned char* s
   int tok;
   if (!do_sample) {
     float mx = -INFINITY;
+#pragma unroll 1
     for (int i = tid; i < V; i += NTHREADS) mx = fmaxf(mx, sv[i]);
-    mx = block_max(mx, red);
+    mx = block_reduce(mx, red, 0);
     int idx = 0x7fffffff;
+#pragma unroll 1
     for (int i = tid; i < V; i += NTHREADS)
       if (sv[i] == mx) idx = min(idx, i);
     tok = block_min_int(idx, ired);
   } else {
     if (top_k > 0 && top_k < V) {
       const float thr = kth_largest(sv, V, top_k, hist, ired);
+#pragma unroll 1
       for (int i = tid; i < V; i += NTHREADS)
         if (sv[i] < thr) sv[i] = -INFINITY;
       __syncthreads();
     }
     float mx = -INFINITY;
+#pragma unroll 1
     for (int i = tid; i < V; i += NTHREADS) mx = fmaxf(mx, sv[i]);
-    mx = block_max(mx, red);
+    mx = block_reduce(mx, red, 0);
     if (top_p < 1.0f) {
       // ascending-order cumulative softmax <= 1-p is removed, highest kept (O(n^2) over the kept set)
       float tot = 0.f;
+#pragma unroll 1
       for (int i = tid; i < V; i += NTHREADS) { const float p = __expf(sv[i] - mx); pv[i] = p; tot += p; }
-      tot = block_sum(tot, red);
+      tot = block_reduce(tot, red, 1);
       __syncthreads();
       unsigned int rm_mask = 0;  // removal flags stay in registers until every thread has finished reading pv/sv
       int slot = 0;
+#pragma unroll 1
       for (int i = tid; i < V; i += NTHREADS, ++slot) {
         const float si = sv[i];
         bool rm = false;
         if (si != -INFINITY) {
           float cum = 0.f;
           bool is_top = true;
+#pragma unroll 1
           for (int j = 0; j < V; ++j) {
             const float sj = sv[j];
             if (sj == -INFINITY) continue;
@@ -720,6 +844,7 @@ __device__ void sample_phase(const Phase& ph, const KParams& P, unsigned char* s
       }
       __syncthreads();
       slot = 0;
+#pragma unroll 1
       for (int i = tid; i < V; i += NTHREADS, ++slot)
         if (rm_mask & (1u << slot)) sv[i] = -INFINITY;
       __syncthreads();
@@ -728,6 +853,7 @@ __device__ void sample_phase(const Phase& ph, const KParams& P, unsigned char* s
     const int E = (V + NTHREADS - 1) / NTHREADS;
     const int i0 = tid * E, i1 = min(V, i0 + E);
     float loc = 0.f;
+#pragma unroll 1
     for (int i = i0; i < i1; ++i) { const float p = __expf(sv[i] - mx); pv[i] = p; loc += p; }
     // block inclusive scan of loc
     float incl = loc;
@@ -741,23 +867,25 @@ __device__ void sample_phase(const Phase& ph, const KParams& P, unsigned char* s
     if (ln == 31) red[wp] = incl;
     __syncthreads();
     float base = 0.f, total = 0.f;
+#pragma unroll 1
     for (int w = 0; w < NWARPS; ++w) { if (w < wp) base += red[w]; total += red[w]; }
     const float excl = base + incl - loc;
-    const float u = philox_uniform(P.sp.seed, (uint32_t)b, (uint32_t)fidx, (uint32_t)ph.group);
+    const float u = philox_uniform(P.sp.seed, (uint32_t)b, (uint32_t)fidx, (uint32_t)group);
     const float target = u * total;
     int cand = 0x7fffffff, lastpos = -1;
     float run = excl;
+#pragma unroll 1
     for (int i = i0; i < i1; ++i) {
       run += pv[i];
       if (pv[i] > 0.f) { lastpos = i; if (run > target && cand == 0x7fffffff) cand = i; }
     }
     cand = block_min_int(cand, ired);
-    if (cand == 0x7fffffff) cand = block_max_int(lastpos, ired);
+    if (cand == 0x7fffffff) cand = -block_min_int(-lastpos, ired);
     tok = cand;
   }
   // teacher forcing (tests)
   if (P.forced && fidx < P.n_forced) {
-    const int f = P.forced[((size_t)b * P.n_forced + fidx) * P.G + ph.group];
+    const int f = P.forced[((size_t)b * P.n_forced + fidx) * P.G + group];
     if (f >= 0) tok = f;
   }
 
@@ -769,23 +897,23 @@ __device__ void sample_phase(const Phase& ph, const KParams& P, unsigned char* s
       if (!was_finished) {
         if (tok == P.eos) { st->finished[b] = 1; st->n_valid[b] = fidx; }
         else { P.seen[(size_t)b * V + tok] = 1; }
-        st->n_gen[b] = ldcgi(&st->n_gen[b]) + 1;
+        st->n_gen[b] = n_gen_b + 1;
       }
       st->c0[b] = tok;
       st->cur[b][0] = tok;
     }
     // CP input for the next frame: token 0 = past_hidden (already saved by the head phase), token 1 = E0[c0]
-    const int B = st->B;
     bf16* x1 = P.x_cp + ((size_t)B + b) * H;
     bf16* x0 = P.x_cp + (size_t)b * H;
     const bf16* e = P.emb_t + (size_t)tok * H;
     const bf16* ph_ = P.past_hidden + (size_t)b * H;
+#pragma unroll 1
     for (int i = tid * 8; i < H; i += NTHREADS * 8) {
       *reinterpret_cast<uint4*>(x1 + i) = *reinterpret_cast<const uint4*>(e + i);
       *reinterpret_cast<uint4*>(x0 + i) = ldcg16(ph_ + i);
     }
   } else {
-    const int j = ph.group;  // codebook index 1..G-1
+    const int j = group;  // codebook index 1..G-1
     if (tid == 0) {
       st->cur[b][j] = tok;
       if (P.codes_out && frame < P.codes_stride) {
@@ -800,17 +928,21 @@ __device__ void sample_phase(const Phase& ph, const KParams& P, unsigned char* s
       // input of the next pass: codec_embedding[j-1](c_j)  (:1281)
       const bf16* e = P.emb_cp + ((size_t)(j - 1) * Vc + tok) * H;
       bf16* x = P.x_cp + (size_t)b * H;
+#pragma unroll 1
       for (int i = tid * 8; i < H; i += NTHREADS * 8)
         *reinterpret_cast<uint4*>(x + i) = *reinterpret_cast<const uint4*>(e + i);
     } else {
       // next talker input: sum of the 16 codebook embeddings (fp32 sum, one bf16 rounding) + text (:1682-1692)
-      const bf16* txt = (frame < st->trailing_len[b])
+      const bf16* txt = (frame < P.trailing_len[b])
                             ? P.trailing + ((size_t)b * P.trailing_stride + frame) * H
                             : P.tts_pad;
-      int codes[Q3_NUM_GROUPS_MAX];
-      for (int g2 = 0; g2 < P.G; ++g2) codes[g2] = (g2 == j) ? tok : ldcgi(&st->cur[b][g2]);
+      int* codes = reinterpret_cast<int*>(hist);  // smem scratch: the 16 codes of this frame
+      if (tid < P.G) codes[tid] = (tid == j) ? tok : ldcgi(&st->cur[b][tid]);
+      __syncthreads();
+#pragma unroll 1
       for (int i = tid; i < H; i += NTHREADS) {
         float s = bf2f(P.emb_t[(size_t)codes[0] * H + i]);
+#pragma unroll 4
         for (int g2 = 1; g2 < P.G; ++g2) s += bf2f(P.emb_cp[((size_t)(g2 - 1) * Vc + codes[g2]) * H + i]);
         P.talker.h[(size_t)b * H + i] = f2bf(rbf(s) + bf2f(txt[i]));
       }
@@ -824,30 +956,68 @@ __device__ void sample_phase(const Phase& ph, const KParams& P, unsigned char* s
 template <int NT>
 __global__ void __launch_bounds__(NTHREADS, 1) q3_program_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ Phase s_ph[2];
+  __shared__ uint4 s_nw[2][256];  // RMSNorm weights of the current / next GEMV phase (<= 2048 bf16)
   DevState* st = P.st;
   unsigned int epoch = 0;  // host resets bar_count to 0 before every launch
+  if (threadIdx.x < (int)(sizeof(Phase) / 4))
+    reinterpret_cast<uint32_t*>(&s_ph[0])[threadIdx.x] = reinterpret_cast<const uint32_t*>(P.prog)[threadIdx.x];
+  __syncthreads();
+  if (s_ph[0].type == PH_GEMV && s_ph[0].norm_w != nullptr && (int)threadIdx.x < s_ph[0].kb * 4)
+    s_nw[0][threadIdx.x] = reinterpret_cast<const uint4*>(s_ph[0].norm_w)[threadIdx.x];
+  __syncthreads();
   const int step_base = st->step;
   int iters_done = 0;
+  int slot = 0;
   const int niter = P.mode == 1 ? P.max_iters : 1;
+#pragma unroll 1
   for (int it = 0; it < niter; ++it) {
     const int frame = step_base + it;
     if (P.mode == 1) {
       bool all = true;
-      for (int b = 0; b < st->B; ++b) all = all && (ldcgi(&st->finished[b]) != 0);
+      for (int b = 0; b < P.B; ++b) all = all && (ldcgi(&st->finished[b]) != 0);
       if (all) break;
     }
+#pragma unroll 1
     for (int pi = 0; pi < P.n_phases; ++pi) {
-      const Phase& ph = P.prog[pi];
-      // pull the next GEMV's weight slice toward L2 while this phase runs / the barrier drains
-      {
-        int nx = pi + 1;
-        if (nx >= P.n_phases && P.mode == 1) nx = 0;
-        if (nx < P.n_phases) prefetch_phase_weights(P.prog[nx]);
-      }
-      if (ph.type == PH_GEMV) gemv_phase<NT>(ph, P, smem);
-      else if (ph.type == PH_ATTN) attn_phase(ph, P, smem, frame);
+      // descriptor pi sits in s_ph[pi & 1] (fetched one phase ahead); fetch pi+1 now, it lands during this phase
+      int nx = pi + 1;
+      if (nx >= P.n_phases) nx = (P.mode == 1) ? 0 : -1;
+      if (nx >= 0 && threadIdx.x < (int)(sizeof(Phase) / 4))
+        reinterpret_cast<uint32_t*>(&s_ph[slot ^ 1])[threadIdx.x] = reinterpret_cast<const uint32_t*>(P.prog + nx)[threadIdx.x];
+      const Phase& ph = s_ph[slot];
+      if (threadIdx.x == 0) g_prof_row = (P.prof && it == 0 && blockIdx.x == 0) ? P.prof + 8 * pi : nullptr;
+      const int type = ph.type;
+      if (type == PH_GEMV) gemv_phase<NT>(ph, P, smem, s_nw[slot]);
+      else if (type == PH_ATTN) attn_phase(ph, P, smem, frame);
       else sample_phase(ph, P, smem, frame, P.mode == 0);
+      __syncthreads();
+      // pull the next GEMV's weight slice toward L2 while the barrier drains, and fetch its norm weights (the
+      // load is issued before the barrier, the smem store happens after it: zero exposed latency)
+      uint4 nwv = make_uint4(0, 0, 0, 0);
+      bool nw_have = false;
+      if (nx >= 0) {
+        const Phase& nph = s_ph[slot ^ 1];
+        prefetch_phase_weights(nph);
+        if (nph.type == PH_GEMV && nph.norm_w != nullptr && (int)threadIdx.x < nph.kb * 4) {
+          nwv = reinterpret_cast<const uint4*>(nph.norm_w)[threadIdx.x];
+          nw_have = true;
+        }
+      }
+      if (P.prof && it == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.prof[8 * pi] = t;
+      }
       grid_barrier(st, epoch);
+      slot ^= 1;
+      if (nw_have) s_nw[slot][threadIdx.x] = nwv;  // visible to the next phase after its first __syncthreads... see below
+      __syncthreads();
+      if (P.prof && it == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        P.prof[8 * pi + 1] = t;
+      }
     }
     ++iters_done;
   }
@@ -898,6 +1068,7 @@ struct q3_engine {
   int trailing_cap = 0;
   size_t trailing_alloc = 0;
   int max_len0 = 0, frames_issued = 0;
+  int len0[MAXB] = {0}, trailing_len[MAXB] = {0};
   unsigned char* seen = nullptr;
   float* split_buf = nullptr;
   Phase* prog_dev = nullptr;
@@ -913,6 +1084,7 @@ struct q3_engine {
   const int* forced = nullptr;
   int n_forced = 0;
   float *dbg_t = nullptr, *dbg_c = nullptr;
+  unsigned long long* prof = nullptr;
   size_t smem_bytes = 0;
   double w_talker_bytes = 0, w_cp_unique_bytes = 0, w_cp_stream_bytes = 0;
 
@@ -979,10 +1151,9 @@ extern "C" int q3_engine_create(const q3_engine_cfg* cfg, q3_engine** out) {
   if (e->alloc(&e->tts_pad, (size_t)H)) return 1;
   if (e->alloc(&e->seen, (size_t)MAXB * cfg->talker.vocab_size)) return 1;
   if (e->alloc(&e->split_buf, (size_t)MAXB * cfg->talker.num_kv_heads * MAXSPLIT * RMAX * 130)) return 1;
-  e->smem_bytes = XS_BYTES + (size_t)NWARPS * 2 * 32 * PCOL * 4 + 1024;
+  e->smem_bytes = smem_bytes_nt(4);
+  static_assert(SAMPLER_SMEM <= ATT_SMEM, "sampler must fit the minimum shared-memory request");
   Q3_REQUIRE(e->smem_bytes <= (size_t)prop.sharedMemPerBlockOptin, "not enough shared memory per block");
-  Q3_REQUIRE((32 * RMAX * HD + 32 * RMAX * 130) * 4 <= XS_BYTES + NWARPS * 2 * 32 * PCOL * 4, "attention smem");
-  Q3_REQUIRE((2 * MAXV + 64 + 256) * 4 <= XS_BYTES, "sampler smem");
   *out = e;
   return 0;
 }
@@ -1150,6 +1321,9 @@ static int build_programs(q3_engine* e, int B) {
     Phase s{}; s.type = PH_SAMPLE; s.group = 0;
     F.push_back(s);
   }
+  for (std::vector<Phase>* pv : {&e->prog_layers, &e->prog_head, &e->prog_frame})
+    for (Phase& p : *pv)
+      if (p.type == PH_GEMV) { p.tq = p.n_tiles / e->sm_count; p.tr = p.n_tiles % e->sm_count; }
   // upload
   const size_t total = e->prog_layers.size() + e->prog_head.size() + F.size();
   if ((int)total > e->prog_cap) {
@@ -1185,9 +1359,9 @@ extern "C" int q3_engine_finalize(q3_engine* e) {
     return 1;
   if (build_programs(e, 1)) return 1;
   // kernel attributes
-  Q3_CUDA(cudaFuncSetAttribute(q3_program_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
-  Q3_CUDA(cudaFuncSetAttribute(q3_program_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
-  Q3_CUDA(cudaFuncSetAttribute(q3_program_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_bytes));
+  Q3_CUDA(cudaFuncSetAttribute(q3_program_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_nt(1)));
+  Q3_CUDA(cudaFuncSetAttribute(q3_program_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_nt(2)));
+  Q3_CUDA(cudaFuncSetAttribute(q3_program_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_nt(4)));
   // algorithmic bytes
   auto lw = [](const q3_stack_cfg& s) {
     return (double)s.hidden_size * (s.num_heads * HD) * 2 + 2.0 * s.hidden_size * (s.num_kv_heads * HD) +
@@ -1210,16 +1384,18 @@ static int launch_program(q3_engine* e, int off, int n, int mode, int max_iters,
   P.prog = e->prog_dev + off; P.n_phases = n; P.mode = mode; P.max_iters = max_iters; P.st = e->st;
   P.talker = e->talker; P.cp = e->cp; P.G = e->cfg.num_code_groups; P.eos = e->cfg.codec_eos_token_id;
   P.has_proj = e->cfg.has_cp_projection; P.sp = e->sp;
+  P.B = e->B;
+  for (int b = 0; b < MAXB; ++b) { P.len0[b] = e->len0[b]; P.trailing_len[b] = e->trailing_len[b]; }
   P.emb_t = e->plain["talker.codec_embedding"]; P.emb_cp = e->plain["cp.codec_embedding"];
   P.x_cp = e->cfg.has_cp_projection ? e->x_cp : e->cp.h; P.past_hidden = e->past_hidden; P.trailing = e->trailing; P.trailing_stride = e->trailing_cap;
   P.tts_pad = e->tts_pad; P.seen = e->seen; P.codes_out = codes_dev; P.codes_stride = e->codes_stride;
-  P.split_buf = e->split_buf; P.forced = e->forced; P.n_forced = e->n_forced; P.dbg_tlogits = e->dbg_t; P.dbg_clogits = e->dbg_c;
+  P.split_buf = e->split_buf; P.forced = e->forced; P.n_forced = e->n_forced; P.dbg_tlogits = e->dbg_t; P.dbg_clogits = e->dbg_c; P.prof = (mode == 1) ? e->prof : nullptr;
   if (chunk) P.chunk = *chunk;
   Q3_CUDA(cudaMemsetAsync(&e->st->bar_count, 0, sizeof(unsigned int), stream));
   void* args[] = {&P};
   const void* fn = nt == 1 ? (const void*)q3_program_kernel<1> : nt == 2 ? (const void*)q3_program_kernel<2>
                                                                         : (const void*)q3_program_kernel<4>;
-  Q3_CUDA(cudaLaunchCooperativeKernel(fn, dim3(e->sm_count), dim3(NTHREADS), args, e->smem_bytes, stream));
+  Q3_CUDA(cudaLaunchCooperativeKernel(fn, dim3(e->sm_count), dim3(NTHREADS), args, (size_t)smem_bytes_nt(nt), stream));
   return 0;
 }
 
@@ -1241,8 +1417,10 @@ extern "C" int q3_prefill(q3_engine* e, int32_t B, const void* embeds_dev, const
   for (int b = 0; b < B; ++b) {
     Q3_REQUIRE(lens_host[b] >= 1 && lens_host[b] < e->cfg.max_ctx, "prompt length %d out of range", lens_host[b]);
     hs.len0[b] = lens_host[b];
+    e->len0[b] = lens_host[b];
     e->max_len0 = b == 0 ? lens_host[b] : std::max(e->max_len0, lens_host[b]);
     hs.trailing_len[b] = trailing_lens_host ? trailing_lens_host[b] : 0;
+    e->trailing_len[b] = hs.trailing_len[b];
     Q3_REQUIRE(hs.trailing_len[b] <= trailing_stride, "trailing length exceeds stride");
   }
   Q3_CUDA(cudaMemcpyAsync(e->st, &hs, sizeof(hs), cudaMemcpyHostToDevice, stream));
@@ -1324,6 +1502,29 @@ extern "C" int q3_set_debug(q3_engine* e, const int32_t* forced_dev, int32_t n_f
   e->forced = forced_dev; e->n_forced = forced_dev ? n_frames : 0;
   e->dbg_t = talker_logits_dev; e->dbg_c = cp_logits_dev;
   return 0;
+}
+
+extern "C" int q3_set_profile(q3_engine* e, unsigned long long* prof_dev) {
+  Q3_REQUIRE(e, "null engine");
+  e->prof = prof_dev;
+  return 0;
+}
+
+// phase kinds of the frame program (0 GEMV, 1 ATTN, 2 SAMPLE) + stack (0 talker, 1 cp) + epilogue, for profiling
+extern "C" int q3_describe_frame_program(q3_engine* e, int32_t* kinds, int32_t capacity) {
+  Q3_REQUIRE(e && e->prog_B > 0, "no program built yet");
+  const int n = (int)e->prog_frame.size();
+  if (kinds) {
+    for (int i = 0; i < n && i < capacity; ++i) {
+      const Phase& p = e->prog_frame[i];
+      int stack = p.stack;
+      if (p.type == PH_GEMV) stack = (p.kb * 32 == e->cfg.talker.hidden_size || p.kb * 32 == e->cfg.talker.intermediate_size ||
+                                      p.kb * 32 == e->cfg.talker.num_heads * HD) && !(p.src == e->cp.h || p.src == e->cp.attn || p.src == e->cp.act) ? 0 : 1;
+      if (p.type == PH_SAMPLE) stack = p.group == 0 ? 0 : 1;
+      kinds[i] = p.type * 100 + stack * 10 + (p.type == PH_GEMV ? p.epi : 0);
+    }
+  }
+  return -n;  // negative = count (0 is reserved for success elsewhere); callers use abs()
 }
 
 extern "C" int q3_algorithmic_bytes(q3_engine* e, int32_t B, int32_t S, double* a_bytes, double* a_stream_bytes) {

@@ -236,6 +236,7 @@ extern "C" void q3_codec_destroy(q3_codec* c) {
 }
 
 extern "C" int q3_codec_total_upsample(q3_codec* c) { return c ? c->total_up : 0; }
+extern "C" int q3_codec_last_launch_count(q3_codec* c) { return c ? c->launches : 0; }
 
 // Engine-native tensors (converted from the reference state_dict by the Python host):
 // shape[] / ndim describe the tensor; dtype is inferred from the name suffix: names ending in ".w" / "table" /

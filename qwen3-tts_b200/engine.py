@@ -167,6 +167,20 @@ class AREngine:
                                          talker_logits.data_ptr() if talker_logits is not None else None,
                                          cp_logits.data_ptr() if cp_logits is not None else None))
 
+    def profile_frame(self, max_frames, codes):
+        """Per-phase device timestamps of the first frame of one decode launch (CTA 0).  Returns
+        (kinds[n], t_phase_end[n], t_barrier_end[n]) in ns."""
+        n = -self.lib.q3_describe_frame_program(self.h, None, 0)
+        kinds = (C.c_int32 * n)()
+        self.lib.q3_describe_frame_program(self.h, kinds, n)
+        buf = torch.zeros(n, 8, dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.q3_set_profile(self.h, buf.data_ptr()))
+        self.decode(max_frames, codes)
+        torch.cuda.current_stream(self.device).synchronize()
+        _lib.check(self.lib.q3_set_profile(self.h, None))
+        t = buf.cpu().numpy()
+        return list(kinds), t[:, 0], t[:, 1], t[:, 2:6]
+
     def algorithmic_bytes(self, B, S):
         a, s = C.c_double(), C.c_double()
         _lib.check(self.lib.q3_algorithmic_bytes(self.h, B, S, C.byref(a), C.byref(s)))

@@ -1,0 +1,58 @@
+"""End-to-end hot path on one GPU: prefill -> fused frame-step decode -> codec decode.
+
+`TTSEngine.synthesize` is the call a user of seam B + seam C makes: prefill embeddings in (host or device),
+waveforms out (host numpy, like Qwen3TTSTokenizer.decode -> `.to(float32).cpu().numpy()`,
+inference/qwen3_tts_tokenizer.py:364)."""
+from typing import List, Sequence
+
+import numpy as np
+import torch
+
+from .codec import CodecDecoder
+from .config import CodecConfig, SamplingParams, TTSConfig
+from .engine import AREngine
+
+
+class TTSEngine:
+    def __init__(self, cfg: TTSConfig, weights, codec_cfg: CodecConfig, codec_weights, device="cuda:0", max_batch=32,
+                 max_ctx=4096, codec_max_frames=1024):
+        self.device = torch.device(device)
+        self.ar = AREngine(cfg, weights, device=device, max_batch=max_batch, max_ctx=max_ctx)
+        self.codec = CodecDecoder(codec_cfg, codec_weights, device=device, max_frames=codec_max_frames, max_batch=max_batch)
+        self.cfg, self.codec_cfg = cfg, codec_cfg
+        self.timing = {}
+
+    @torch.no_grad()
+    def generate_codes(self, inputs_embeds, trailing_text, tts_pad_embed, sp: SamplingParams) -> List[torch.Tensor]:
+        return self.ar.generate(inputs_embeds, trailing_text, tts_pad_embed, sp)
+
+    @torch.no_grad()
+    def decode_codes(self, codes: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        """List[(T_i,K)] -> List[(T_i*1920,)] fp32 on device; == Qwen3TTSTokenizer.decode's padding with -1 +
+        Qwen3TTSTokenizerV2Model.decode (inference/qwen3_tts_tokenizer.py:329, …v2.py:993-1024)."""
+        B = len(codes)
+        Tm = max(max(int(c.shape[0]) for c in codes), 1)
+        K = self.codec_cfg.num_quantizers
+        ac = torch.full((B, Tm, K), -1, dtype=torch.int64, device=self.device)
+        for i, c in enumerate(codes):
+            ac[i, :c.shape[0]] = c.to(self.device)
+        return self.codec.decode(ac)
+
+    @torch.no_grad()
+    def synthesize(self, inputs_embeds, trailing_text, tts_pad_embed, sp: SamplingParams, to_host=True):
+        """inputs_embeds / trailing_text / tts_pad_embed may live in (pinned) host memory: they are copied to the
+        device here, and the waveforms are copied back — both inside the caller's timed region."""
+        dev = self.device
+        emb = [e.to(dev, non_blocking=True) for e in inputs_embeds]
+        tr = [t.to(dev, non_blocking=True) for t in trailing_text]
+        pad = tts_pad_embed.to(dev, non_blocking=True)
+        codes = self.ar.generate(emb, tr, pad, sp)
+        wavs = self.decode_codes(codes)
+        if not to_host:
+            return wavs, codes
+        out = [w.to(torch.float32).cpu().numpy() for w in wavs]
+        return out, codes
+
+    def close(self):
+        self.ar.close()
+        self.codec.close()
