@@ -1,0 +1,106 @@
+"""Mint golden vectors from the REFERENCE's own modules (through oracle/ref_shims.py) and commit them under
+tests/golden/.  Run in the build container only:  python -m oracle.make_golden
+
+The reference ships no fixtures; these pin the oracle wherever /root/reference is absent (GPU box).
+Shapes are deliberately micro (weights travel inside the .npz)."""
+import os
+
+import numpy as np
+import torch
+
+from . import codec as OC
+from . import ref_driver as R
+from . import talker as OT
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def micro_tts_cfg():
+    V = 1200
+    return OT.TTSCfg(talker=OT.StackCfg(64, 2, 2, 1, 32, 128, V, rope_theta=1e6),
+                     cp=OT.StackCfg(32, 2, 2, 1, 32, 64, 64, rope_theta=1e4), text_hidden_size=64, text_vocab_size=100,
+                     codec_eos_token_id=V - 10, codec_pad_id=V - 12, codec_bos_id=V - 11, tts_bos_token_id=97,
+                     tts_eos_token_id=98, tts_pad_token_id=96)
+
+
+def micro_codec_cfg():
+    return OC.CodecCfg(codebook_size=32, codebook_dim=16, hidden_size=32, latent_dim=32, num_heads=2, num_kv_heads=2,
+                       head_dim=16, sliding_window=4, intermediate_size=48, num_layers=2, num_quantizers=16,
+                       upsample_rates=(8, 5, 4, 3), upsampling_ratios=(2, 2), decoder_dim=48)
+
+
+def make_talker():
+    from transformers.cache_utils import DynamicCache
+    cfg = micro_tts_cfg()
+    W = OT.random_weights(cfg, seed=11, with_text=False)
+    m = R.build_reference_talker(cfg, text_vocab=100)
+    R.load_weights_into_reference(m, {k: v for k, v in W.items()})
+    g = torch.Generator().manual_seed(5)
+    H, B, lens, N, G = 64, 2, [4, 7], 4, 16
+    embs = [torch.randn(l, H, generator=g) * 0.5 for l in lens]
+    trail = [torch.randn(n, H, generator=g) * 0.1 for n in (2, 0)]
+    pad = torch.randn(H, generator=g) * 0.1
+    codes = torch.randint(0, 64, (B, N, G), generator=g)
+    codes[:, :, 0] = torch.randint(0, 150, (B, N), generator=g)
+    Lmax = max(lens)
+    x = torch.zeros(B, Lmax, H)
+    mask = torch.zeros(B, Lmax, dtype=torch.long)
+    for i, e in enumerate(embs):
+        x[i, Lmax - len(e):] = e
+        mask[i, Lmax - len(e):] = 1
+    cache = DynamicCache()
+    m.rope_deltas = None
+    tl, cl = [], []
+    with torch.no_grad():
+        out = m(inputs_embeds=x, attention_mask=mask, past_key_values=cache, use_cache=True, cache_position=torch.arange(Lmax))
+        tl.append(out.logits[:, -1].numpy().copy())
+        past_hidden = out.past_hidden
+        for step in range(N):
+            c0 = codes[:, step, 0]
+            cpc = DynamicCache()
+            e0 = m.get_input_embeddings()(c0[:, None])
+            o = m.code_predictor(inputs_embeds=torch.cat((past_hidden, e0), dim=1), past_key_values=cpc, use_cache=True)
+            cl.append(o.logits[:, -1].numpy().copy())
+            gs = o.generation_steps
+            for j in range(1, G - 1):
+                o = m.code_predictor(input_ids=codes[:, step, j:j + 1], past_key_values=cpc, use_cache=True, generation_steps=gs)
+                gs = o.generation_steps
+                cl.append(o.logits[:, -1].numpy().copy())
+            hid = [e0] + [m.code_predictor.get_input_embeddings()[i](codes[:, step, i + 1:i + 2]) for i in range(G - 1)]
+            xe = torch.cat(hid, dim=1).sum(1, keepdim=True)
+            tr = torch.stack([t[step] if step < t.shape[0] else pad for t in trail])[:, None]
+            xe = xe + tr
+            mask = torch.cat((mask, torch.ones(B, 1, dtype=torch.long)), dim=1)
+            cp = torch.tensor([Lmax + step])
+            pos = (cp[0] + m.rope_deltas).view(1, B, 1).expand(3, -1, -1)
+            mo = m.model(inputs_embeds=xe, attention_mask=mask, position_ids=pos, past_key_values=cache, use_cache=True, cache_position=cp)
+            past_hidden = mo.last_hidden_state[:, -1:]
+            tl.append(m.codec_head(mo.last_hidden_state)[:, -1].numpy().copy())
+    blob = {f"W::{k}": v.numpy() for k, v in W.items()}
+    blob.update({f"emb{i}": e.numpy() for i, e in enumerate(embs)})
+    blob.update({f"trail{i}": t.numpy() for i, t in enumerate(trail)})
+    blob.update(pad=pad.numpy(), codes=codes.numpy(), talker_logits=np.stack(tl), cp_logits=np.stack(cl))
+    np.savez_compressed(os.path.join(OUT, "talker_micro.npz"), **blob)
+    print("talker_micro.npz", np.stack(tl).shape, np.stack(cl).shape)
+
+
+def make_codec():
+    cfg = micro_codec_cfg()
+    W = OC.random_weights(cfg, seed=13)
+    m = R.build_reference_codec_decoder(cfg)
+    m.load_state_dict(W, strict=False)
+    g = torch.Generator().manual_seed(2)
+    codes = torch.randint(0, cfg.codebook_size, (2, 16, 9), generator=g)
+    with torch.no_grad():
+        wav = m(codes)
+        wav_c = m.chunked_decode(codes, chunk_size=4, left_context_size=2)
+    blob = {f"W::{k}": v.numpy() for k, v in W.items()}
+    blob.update(codes=codes.numpy(), wav=wav.numpy(), wav_chunked=wav_c.numpy())
+    np.savez_compressed(os.path.join(OUT, "codec_micro.npz"), **blob)
+    print("codec_micro.npz", wav.shape, float(wav.abs().max()))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    make_talker()
+    make_codec()

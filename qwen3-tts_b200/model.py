@@ -1,0 +1,455 @@
+"""Host-side mirror of the reference's Python API on top of the B200 engines (drop-in boundary).
+
+  * `Qwen3TTSForConditionalGenerationB200.generate(...)`  == core/models/modeling_qwen3_tts.py:2022-2292 (a1): builds the
+    per-sample prefill embeddings exactly as the reference does (role / think-language-speaker prefix / text / ICL,
+    SURVEY App. A.1) with plain PyTorch ops, then hands them to the fused AR engine (seam B) instead of
+    `talker.generate`, and returns the per-sample code lists trimmed at the first EOS.
+  * `Qwen3TTSModel`      == inference/qwen3_tts_model.py:54 (generate_custom_voice / voice_design / voice_clone).
+  * `Qwen3TTSTokenizer`  == inference/qwen3_tts_tokenizer.py:44 (decode(); encode() needs the Mimi encoder).
+
+No checkpoints/tokenizers exist offline, so construction takes the loaded state_dict + config + a `processor`
+callable (`processor(text=..., return_tensors="pt")["input_ids"]`, i.e. the HF Qwen2 tokenizer in production).
+"""
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .codec import CodecDecoder
+from .config import CodecConfig, SamplingParams, TTSConfig
+from .engine import AREngine
+
+
+@dataclass
+class VoiceClonePromptItem:
+    """inference/qwen3_tts_model.py:40-51."""
+    ref_code: Optional[torch.Tensor]
+    ref_spk_embedding: torch.Tensor
+    x_vector_only_mode: bool
+    icl_mode: bool
+    ref_text: Optional[str] = None
+
+
+class Qwen3TTSForConditionalGenerationB200:
+    def __init__(self, cfg: TTSConfig, weights: Dict[str, torch.Tensor], device="cuda:0", spk_id=None,
+                 spk_is_dialect=None, codec_language_id=None, tts_model_type="custom_voice", tts_model_size="1b7",
+                 max_batch=32, max_ctx=4096, engine: Optional[AREngine] = None):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.dtype = torch.bfloat16
+        self.spk_id = {k.lower(): v for k, v in (spk_id or {}).items()}
+        self.spk_is_dialect = {k.lower(): v for k, v in (spk_is_dialect or {}).items()}
+        self.codec_language_id = {k.lower(): v for k, v in (codec_language_id or {}).items()}
+        self.tts_model_type, self.tts_model_size = tts_model_type, tts_model_size
+        g = lambda n: weights[n].detach().to(self.device, self.dtype)  # noqa: E731
+        self.text_embedding = g("talker.model.text_embedding.weight")
+        self.fc1_w, self.fc1_b = g("talker.text_projection.linear_fc1.weight"), g("talker.text_projection.linear_fc1.bias")
+        self.fc2_w, self.fc2_b = g("talker.text_projection.linear_fc2.weight"), g("talker.text_projection.linear_fc2.bias")
+        self.codec_embedding = g("talker.model.codec_embedding.weight")
+        self.cp_embeddings = [g(f"talker.code_predictor.model.codec_embedding.{j}.weight")
+                              for j in range(cfg.num_code_groups - 1)]
+        self.engine = engine or AREngine(cfg, weights, device=device, max_batch=max_batch, max_ctx=max_ctx)
+        self.speech_tokenizer = None
+        self.generate_config = None
+        self.supported_speakers = self.spk_id.keys()
+        self.supported_languages = ["auto"] + [k for k in self.codec_language_id if "dialect" not in k]
+
+    # -- small helpers restating the reference's embedding calls
+    def _tp(self, ids: torch.Tensor) -> torch.Tensor:
+        """text_projection(text_embedding(ids)) — ResizeMLP: Linear(bias) -> SiLU -> Linear(bias) (:808-816)."""
+        x = F.embedding(ids.to(self.device), self.text_embedding)
+        return F.linear(F.silu(F.linear(x, self.fc1_w, self.fc1_b)), self.fc2_w, self.fc2_b)
+
+    def _ce(self, ids) -> torch.Tensor:
+        return F.embedding(torch.as_tensor(ids, device=self.device, dtype=torch.long), self.codec_embedding)
+
+    def load_speech_tokenizer(self, speech_tokenizer):
+        self.speech_tokenizer = speech_tokenizer
+
+    def load_generate_config(self, generate_config):
+        self.generate_config = generate_config
+
+    def get_supported_speakers(self):
+        return self.supported_speakers
+
+    def get_supported_languages(self):
+        return self.supported_languages
+
+    def generate_icl_prompt(self, text_id, ref_id, ref_code, tts_pad_embed, tts_eos_embed, non_streaming_mode):
+        """:1968-2019."""
+        text_embed = self._tp(torch.cat([ref_id, text_id], dim=-1))
+        text_embed = torch.cat([text_embed, tts_eos_embed], dim=1)
+        ref_code = ref_code.to(self.device)
+        parts = [F.embedding(ref_code[:, :1], self.codec_embedding)]
+        for i in range(1, self.cfg.num_code_groups):
+            parts.append(F.embedding(ref_code[:, i:i + 1], self.cp_embeddings[i - 1]))
+        codec_embed = torch.cat(parts, dim=1).sum(1).unsqueeze(0)
+        codec_embed = torch.cat([self._ce([[self.cfg.codec_bos_id]]), codec_embed], dim=1)
+        text_lens, codec_lens = text_embed.shape[1], codec_embed.shape[1]
+        if non_streaming_mode:
+            icl = text_embed + self._ce([[self.cfg.codec_pad_id] * text_lens])
+            icl = torch.cat([icl, codec_embed + tts_pad_embed], dim=1)
+            return icl, tts_pad_embed
+        if text_lens > codec_lens:
+            return text_embed[:, :codec_lens] + codec_embed, text_embed[:, codec_lens:]
+        text_embed = torch.cat([text_embed] + [tts_pad_embed] * (codec_lens - text_lens), dim=1)
+        return text_embed + codec_embed, tts_pad_embed
+
+    @torch.no_grad()
+    def build_prefill(self, input_ids, instruct_ids=None, ref_ids=None, voice_clone_prompt=None, languages=None,
+                      speakers=None, non_streaming_mode=False):
+        """:2068-2237 — per-sample (unpadded) prefill embeddings + trailing text + tts_pad.  The reference's left
+        padding / attention mask (:2239-2254) is not materialised: the engine takes per-sequence lengths."""
+        cfg = self.cfg
+        n = len(input_ids)
+        pieces: List[List[torch.Tensor]] = [[] for _ in range(n)]
+        spk_embeds = None
+        if voice_clone_prompt is not None:
+            spk_embeds = [e.to(self.device).to(self.dtype) for e in voice_clone_prompt["ref_spk_embedding"]]
+        if instruct_ids is not None:
+            for i, ins in enumerate(instruct_ids):
+                if ins is not None:
+                    pieces[i].append(self._tp(ins))
+        trailing = []
+        if speakers is None:
+            speakers = [None] * n
+        tts_pad_embed = None
+        for index, (input_id, language, speaker) in enumerate(zip(input_ids, languages, speakers)):
+            input_id = input_id.to(self.device)
+            if spk_embeds is None:
+                if speaker == "" or speaker is None:
+                    speaker_embed = None
+                else:
+                    if speaker.lower() not in self.spk_id:
+                        raise NotImplementedError(f"Speaker {speaker} not implemented")
+                    speaker_embed = self._ce(self.spk_id[speaker.lower()])
+            else:
+                if voice_clone_prompt["x_vector_only_mode"][index] or voice_clone_prompt["icl_mode"][index]:
+                    speaker_embed = spk_embeds[index]
+                else:
+                    speaker_embed = None
+            assert language is not None
+            if language.lower() == "auto":
+                language_id = None
+            else:
+                if language.lower() not in self.codec_language_id:
+                    raise NotImplementedError(f"Language {language} not implemented")
+                language_id = self.codec_language_id[language.lower()]
+            if (language.lower() in ["chinese", "auto"] and speaker != "" and speaker is not None
+                    and self.spk_is_dialect.get(speaker.lower(), False) is not False):
+                language_id = self.codec_language_id[self.spk_is_dialect[speaker.lower()]]
+            tts_bos_embed, tts_eos_embed, tts_pad_embed = self._tp(torch.tensor(
+                [[cfg.tts_bos_token_id, cfg.tts_eos_token_id, cfg.tts_pad_token_id]], device=self.device)).chunk(3, dim=1)
+            if language_id is None:
+                prefill = [[cfg.codec_nothink_id, cfg.codec_think_bos_id, cfg.codec_think_eos_id]]
+            else:
+                prefill = [[cfg.codec_think_id, cfg.codec_think_bos_id, language_id, cfg.codec_think_eos_id]]
+            e0 = self._ce(prefill)
+            e1 = self._ce([[cfg.codec_pad_id, cfg.codec_bos_id]])
+            if speaker_embed is None:
+                codec_in = torch.cat([e0, e1], dim=1)
+            else:
+                codec_in = torch.cat([e0, speaker_embed.view(1, 1, -1), e1], dim=1)
+            role = self._tp(input_id[:, :3])
+            overlay = torch.cat((tts_pad_embed.expand(-1, codec_in.shape[1] - 2, -1), tts_bos_embed), dim=1) + codec_in[:, :-1]
+            emb = torch.cat((role, overlay), dim=1)
+            if (voice_clone_prompt is not None and voice_clone_prompt["ref_code"] is not None
+                    and voice_clone_prompt["icl_mode"][index]):
+                icl, trail = self.generate_icl_prompt(input_id[:, 3:-5], ref_ids[index][:, 3:-2].to(self.device),
+                                                      voice_clone_prompt["ref_code"][index], tts_pad_embed, tts_eos_embed,
+                                                      non_streaming_mode)
+                emb = torch.cat([emb, icl], dim=1)
+            else:
+                emb = torch.cat([emb, self._tp(input_id[:, 3:4]) + codec_in[:, -1:]], dim=1)
+                if non_streaming_mode:
+                    emb = emb[:, :-1]
+                    T = input_id[:, 3:-5].shape[1]
+                    emb = torch.cat([emb,
+                                     torch.cat((self._tp(input_id[:, 3:-5]), tts_eos_embed), dim=1)
+                                     + self._ce([[cfg.codec_pad_id] * (T + 1)]),
+                                     tts_pad_embed + self._ce([[cfg.codec_bos_id]])], dim=1)
+                    trail = tts_pad_embed
+                else:
+                    trail = torch.cat((self._tp(input_id[:, 4:-5]), tts_eos_embed), dim=1)
+            pieces[index].append(emb)
+            trailing.append(trail)
+        embeds = [torch.cat(p, dim=1).squeeze(0) for p in pieces]
+        trailing = [t.squeeze(0) for t in trailing]
+        return embeds, trailing, tts_pad_embed.reshape(-1)
+
+    @torch.no_grad()
+    def generate(self, input_ids=None, instruct_ids=None, ref_ids=None, voice_clone_prompt=None, languages=None,
+                 speakers=None, non_streaming_mode=False, max_new_tokens: int = 4096, do_sample: bool = True,
+                 top_k: int = 50, top_p: float = 1.0, temperature: float = 0.9, subtalker_dosample: bool = True,
+                 subtalker_top_k: int = 50, subtalker_top_p: float = 1.0, subtalker_temperature: float = 0.9,
+                 eos_token_id: Optional[int] = None, repetition_penalty: float = 1.05, seed: int = 0, **kwargs):
+        """Signature and return of :2022-2043 / :2292.  The second return value (per-step hidden states) is not
+        produced by the fused engine; the reference's own wrappers discard it."""
+        embeds, trailing, pad = self.build_prefill(input_ids, instruct_ids, ref_ids, voice_clone_prompt, languages,
+                                                   speakers, non_streaming_mode)
+        if eos_token_id is not None and eos_token_id != self.cfg.codec_eos_token_id:
+            raise ValueError("eos_token_id must equal config.talker_config.codec_eos_token_id in the fused engine")
+        sp = SamplingParams(do_sample=do_sample, top_k=top_k, top_p=top_p, temperature=temperature,
+                            repetition_penalty=repetition_penalty, subtalker_dosample=subtalker_dosample,
+                            subtalker_top_k=subtalker_top_k, subtalker_top_p=subtalker_top_p,
+                            subtalker_temperature=subtalker_temperature, min_new_tokens=2, max_new_tokens=max_new_tokens,
+                            seed=seed)
+        tr = trailing
+        out: List[torch.Tensor] = []
+        mb = self.engine.max_batch
+        for s in range(0, len(embeds), mb):  # the reference runs one padded batch; we tile by engine capacity
+            out += self.engine.generate(embeds[s:s + mb], tr[s:s + mb], pad, sp)
+        return out, [None] * len(out)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+class Qwen3TTSTokenizer:
+    """inference/qwen3_tts_tokenizer.py:44 — decode path on the B200 codec engine."""
+
+    def __init__(self, cfg: CodecConfig, weights, device="cuda:0", max_frames=1024):
+        self.config = cfg
+        self.device = torch.device(device)
+        self.decoder = CodecDecoder(cfg, weights, device=device, max_frames=max_frames)
+
+    def get_model_type(self):
+        return "qwen3_tts_tokenizer_12hz"
+
+    def get_input_sample_rate(self):
+        return 24000
+
+    def get_output_sample_rate(self):
+        return 24000
+
+    def get_encode_downsample_rate(self):
+        return self.config.total_upsample
+
+    def get_decode_upsample_rate(self):
+        return self.config.total_upsample
+
+    def encode(self, audios, sr=None, return_dict=True):
+        raise NotImplementedError("codec ENCODER (transformers MimiModel, third-party) is a 'next' row (SURVEY §8f-1); "
+                                  "use the reference encoder and pass its audio_codes to decode()")
+
+    def decode(self, encoded) -> Tuple[List[np.ndarray], int]:
+        """:259-365 — accepts an encode()-style output (has .audio_codes), a dict or a list of dicts whose
+        "audio_codes" is a (T,K) tensor / ndarray; pads with -1, decodes, trims to T_i*1920, returns float32 numpy."""
+        if hasattr(encoded, "audio_codes"):
+            codes_list = list(encoded.audio_codes)
+        elif isinstance(encoded, dict):
+            codes_list = [encoded["audio_codes"]] if "audio_codes" in encoded else None
+        elif isinstance(encoded, list):
+            codes_list = [e["audio_codes"] for e in encoded]
+        else:
+            raise TypeError("`encoded` must be an encode output, a dict, or a list of dicts.")
+        if codes_list is None:
+            raise ValueError("`encoded` dict must contain 'audio_codes'.")
+        tens = []
+        for c in codes_list:
+            if isinstance(c, np.ndarray):
+                c = torch.from_numpy(c)
+            if not isinstance(c, torch.Tensor):
+                raise TypeError("audio_codes must be a torch.Tensor or np.ndarray")
+            if c.dim() != 2:
+                raise ValueError(f"audio_codes must have shape (T, K), got {tuple(c.shape)}")
+            tens.append(c.to(self.device, torch.long))
+        Tm = max(int(c.shape[0]) for c in tens)
+        K = tens[0].shape[1]
+        ac = torch.full((len(tens), max(Tm, 1), K), -1, dtype=torch.long, device=self.device)
+        for i, c in enumerate(tens):
+            ac[i, :c.shape[0]] = c
+        wavs = self.decoder.decode(ac)
+        return [w.to(torch.float32).detach().cpu().numpy() for w in wavs], 24000
+
+
+class Qwen3TTSModel:
+    """inference/qwen3_tts_model.py:54 — same entry points, input normalisation, kwarg precedence and returns."""
+
+    def __init__(self, model: Qwen3TTSForConditionalGenerationB200, processor, generate_defaults: Optional[dict] = None):
+        self.model = model
+        self.processor = processor
+        self.generate_defaults = generate_defaults or {}
+        self.device = model.device
+
+    # ---- helpers (:207-352)
+    @staticmethod
+    def _ensure_list(x):
+        return x if isinstance(x, list) else [x]
+
+    @staticmethod
+    def _build_assistant_text(text):
+        return f"<|im_start|>assistant\n{text}<|im_end|>\n<|im_start|>assistant\n"
+
+    @staticmethod
+    def _build_ref_text(text):
+        return f"<|im_start|>assistant\n{text}<|im_end|>\n"
+
+    @staticmethod
+    def _build_instruct_text(instruct):
+        return f"<|im_start|>user\n{instruct}<|im_end|>\n"
+
+    def _tokenize_texts(self, texts):
+        out = []
+        for text in texts:
+            ids = self.processor(text=text, return_tensors="pt", padding=True)["input_ids"].to(self.device)
+            out.append(ids.unsqueeze(0) if ids.dim() == 1 else ids)
+        return out
+
+    def _merge_generate_kwargs(self, **kw) -> Dict[str, Any]:
+        hard = dict(do_sample=True, top_k=50, top_p=1.0, temperature=0.9, repetition_penalty=1.05,
+                    subtalker_dosample=True, subtalker_top_k=50, subtalker_top_p=1.0, subtalker_temperature=0.9,
+                    max_new_tokens=2048)
+        merged = {k: v for k, v in kw.items() if k not in hard}
+        for name, dv in hard.items():
+            uv = kw.get(name)
+            merged[name] = uv if uv is not None else self.generate_defaults.get(name, dv)
+        return merged
+
+    def _supported_languages_set(self):
+        s = self.model.get_supported_languages()
+        return None if s is None else {x.lower() for x in s}
+
+    def _supported_speakers_set(self):
+        s = self.model.get_supported_speakers()
+        return None if s is None else {x.lower() for x in s}
+
+    def _validate_languages(self, languages):
+        sup = self._supported_languages_set()
+        if sup is None:
+            return
+        bad = [l for l in languages if l is None or l.lower() not in sup]
+        if bad:
+            raise ValueError(f"Unsupported languages: {bad}. Supported: {sorted(sup)}")
+
+    def _validate_speakers(self, speakers):
+        sup = self._supported_speakers_set()
+        if sup is None:
+            return
+        bad = [s for s in speakers if s is not None and s != "" and s.lower() not in sup]
+        if bad:
+            raise ValueError(f"Unsupported speakers: {bad}. Supported: {sorted(sup)}")
+
+    def get_supported_speakers(self):
+        s = self._supported_speakers_set()
+        return None if s is None else sorted(s)
+
+    def get_supported_languages(self):
+        s = self._supported_languages_set()
+        return None if s is None else sorted(s)
+
+    def _broadcast(self, texts, *lists):
+        out = []
+        for l in lists:
+            if len(l) == 1 and len(texts) > 1:
+                l = l * len(texts)
+            out.append(l)
+        return out
+
+    def _decode(self, codes_list):
+        return self.model.speech_tokenizer.decode([{"audio_codes": c} for c in codes_list])
+
+    # ---- :731-839
+    def generate_custom_voice(self, text, speaker, language=None, instruct=None, non_streaming_mode=True, **kwargs):
+        if self.model.tts_model_type != "custom_voice":
+            raise ValueError(f"model type {self.model.tts_model_type} does not support generate_custom_voice")
+        texts = self._ensure_list(text)
+        languages = self._ensure_list(language) if isinstance(language, list) else (
+            [language] * len(texts) if language is not None else ["Auto"] * len(texts))
+        speakers = self._ensure_list(speaker)
+        if self.model.tts_model_size in "0b6":
+            instruct = None
+        instructs = self._ensure_list(instruct) if isinstance(instruct, list) else (
+            [instruct] * len(texts) if instruct is not None else [""] * len(texts))
+        languages, speakers, instructs = self._broadcast(texts, languages, speakers, instructs)
+        if not (len(texts) == len(languages) == len(speakers) == len(instructs)):
+            raise ValueError(f"Batch size mismatch: text={len(texts)}, language={len(languages)}, "
+                             f"speaker={len(speakers)}, instruct={len(instructs)}")
+        self._validate_languages(languages)
+        self._validate_speakers(speakers)
+        input_ids = self._tokenize_texts([self._build_assistant_text(t) for t in texts])
+        instruct_ids = [None if (i is None or i == "") else self._tokenize_texts([self._build_instruct_text(i)])[0]
+                        for i in instructs]
+        codes, _ = self.model.generate(input_ids=input_ids, instruct_ids=instruct_ids, languages=languages,
+                                       speakers=speakers, non_streaming_mode=non_streaming_mode,
+                                       **self._merge_generate_kwargs(**kwargs))
+        return self._decode(codes)
+
+    # ---- :636-728
+    def generate_voice_design(self, text, instruct, language=None, non_streaming_mode=True, **kwargs):
+        if self.model.tts_model_type != "voice_design":
+            raise ValueError(f"model type {self.model.tts_model_type} does not support generate_voice_design")
+        texts = self._ensure_list(text)
+        languages = self._ensure_list(language) if isinstance(language, list) else (
+            [language] * len(texts) if language is not None else ["Auto"] * len(texts))
+        instructs = self._ensure_list(instruct)
+        languages, instructs = self._broadcast(texts, languages, instructs)
+        if not (len(texts) == len(languages) == len(instructs)):
+            raise ValueError(f"Batch size mismatch: text={len(texts)}, language={len(languages)}, instruct={len(instructs)}")
+        self._validate_languages(languages)
+        input_ids = self._tokenize_texts([self._build_assistant_text(t) for t in texts])
+        instruct_ids = [None if (i is None or i == "") else self._tokenize_texts([self._build_instruct_text(i)])[0]
+                        for i in instructs]
+        codes, _ = self.model.generate(input_ids=input_ids, instruct_ids=instruct_ids, languages=languages,
+                                       non_streaming_mode=non_streaming_mode, **self._merge_generate_kwargs(**kwargs))
+        return self._decode(codes)
+
+    # ---- :355-458 — needs the codec ENCODER and the speaker encoder ("next" rows): prompts must be supplied
+    def create_voice_clone_prompt(self, ref_audio, ref_text=None, x_vector_only_mode=False):
+        raise NotImplementedError("create_voice_clone_prompt needs the Mimi codec encoder and the ECAPA speaker encoder "
+                                  "(SURVEY §8f rows 1/3); build VoiceClonePromptItem with the reference and pass it in")
+
+    @staticmethod
+    def _prompt_items_to_voice_clone_prompt(items: List[VoiceClonePromptItem]) -> Dict[str, Any]:
+        return dict(ref_code=[it.ref_code for it in items], ref_spk_embedding=[it.ref_spk_embedding for it in items],
+                    x_vector_only_mode=[it.x_vector_only_mode for it in items], icl_mode=[it.icl_mode for it in items])
+
+    # ---- :469-633
+    def generate_voice_clone(self, text, language=None, ref_audio=None, ref_text=None, x_vector_only_mode=False,
+                             voice_clone_prompt=None, non_streaming_mode=False, **kwargs):
+        if self.model.tts_model_type != "base":
+            raise ValueError(f"model type {self.model.tts_model_type} does not support generate_voice_clone")
+        texts = self._ensure_list(text)
+        languages = self._ensure_list(language) if isinstance(language, list) else (
+            [language] * len(texts) if language is not None else ["Auto"] * len(texts))
+        (languages,) = self._broadcast(texts, languages)
+        if len(texts) != len(languages):
+            raise ValueError(f"Batch size mismatch: text={len(texts)}, language={len(languages)}")
+        self._validate_languages(languages)
+        if voice_clone_prompt is None:
+            if ref_audio is None:
+                raise ValueError("Either `voice_clone_prompt` or `ref_audio` must be provided.")
+            voice_clone_prompt = self.create_voice_clone_prompt(ref_audio, ref_text, x_vector_only_mode)
+        if isinstance(voice_clone_prompt, list):
+            items = voice_clone_prompt
+            if len(items) == 1 and len(texts) > 1:
+                items = items * len(texts)
+            if len(items) != len(texts):
+                raise ValueError(f"Batch size mismatch: prompt={len(items)}, text={len(texts)}")
+            vcp = self._prompt_items_to_voice_clone_prompt(items)
+            ref_texts = [it.ref_text for it in items]
+        else:
+            vcp, ref_texts = voice_clone_prompt, None
+        input_ids = self._tokenize_texts([self._build_assistant_text(t) for t in texts])
+        ref_ids = None
+        if ref_texts is not None:
+            ref_ids = [None if (rt is None or rt == "") else self._tokenize_texts([self._build_ref_text(rt)])[0]
+                       for rt in ref_texts]
+        codes, _ = self.model.generate(input_ids=input_ids, ref_ids=ref_ids, voice_clone_prompt=vcp, languages=languages,
+                                       non_streaming_mode=non_streaming_mode, **self._merge_generate_kwargs(**kwargs))
+        ref_codes = vcp.get("ref_code", None)
+        full = []
+        for i, c in enumerate(codes):
+            if ref_codes is not None and ref_codes[i] is not None:
+                full.append(torch.cat([ref_codes[i].to(c.device), c], dim=0))
+            else:
+                full.append(c)
+        wavs, fs = self._decode(full)
+        out = []
+        for i, wav in enumerate(wavs):
+            if ref_codes is not None and ref_codes[i] is not None:
+                cut = int(int(ref_codes[i].shape[0]) / max(int(full[i].shape[0]), 1) * wav.shape[0])
+                out.append(wav[cut:])
+            else:
+                out.append(wav)
+        return out, fs

@@ -1,0 +1,74 @@
+"""Public wrapper semantics (inference/qwen3_tts_model.py) with a fake engine: input broadcasting, validation,
+kwarg precedence, voice-clone proportional cut — no GPU needed."""
+import numpy as np
+import pytest
+import torch
+
+from qwen3_tts_b200.model import Qwen3TTSModel, VoiceClonePromptItem
+
+
+class _FakeTok:
+    def decode(self, items):
+        return [np.arange(int(d["audio_codes"].shape[0]) * 1920, dtype=np.float32) for d in items], 24000
+
+
+class _FakeCore:
+    tts_model_type = "custom_voice"
+    tts_model_size = "1b7"
+    device = torch.device("cpu")
+
+    def __init__(self):
+        self.calls = []
+        self.speech_tokenizer = _FakeTok()
+
+    def get_supported_speakers(self):
+        return ["Alice", "bob"]
+
+    def get_supported_languages(self):
+        return ["auto", "english", "chinese"]
+
+    def generate(self, **kw):
+        self.calls.append(kw)
+        n = len(kw["input_ids"])
+        return [torch.zeros(4 + i, 16, dtype=torch.long) for i in range(n)], [None] * n
+
+
+def _proc(text=None, return_tensors="pt", padding=True):
+    return {"input_ids": torch.tensor([[1, 2, 3] + [ord(c) % 50 for c in text][:8] + [4, 5, 6, 7, 8]])}
+
+
+def test_custom_voice_broadcast_defaults_and_validation():
+    core = _FakeCore()
+    m = Qwen3TTSModel(core, _proc, generate_defaults={"top_k": 20, "temperature": 0.7})
+    wavs, fs = m.generate_custom_voice(["hello", "world"], speaker="alice", language="English", top_k=None, temperature=0.5)
+    assert fs == 24000 and [w.shape[0] for w in wavs] == [4 * 1920, 5 * 1920]
+    kw = core.calls[-1]
+    assert kw["speakers"] == ["alice", "alice"] and kw["languages"] == ["English", "English"]
+    assert kw["instruct_ids"] == [None, None] and kw["non_streaming_mode"] is True
+    # precedence: user > generate_config.json > hard defaults (:287-352)
+    assert kw["top_k"] == 20 and kw["temperature"] == 0.5 and kw["repetition_penalty"] == 1.05 and kw["max_new_tokens"] == 2048
+    with pytest.raises(ValueError):
+        m.generate_custom_voice("x", speaker="carol")
+    with pytest.raises(ValueError):
+        m.generate_custom_voice("x", speaker="alice", language="klingon")
+    with pytest.raises(ValueError):
+        m.generate_custom_voice(["a", "b", "c"], speaker=["alice", "bob"])
+    with pytest.raises(ValueError):
+        m.generate_voice_design("x", instruct="y")  # wrong model type
+    assert m.get_supported_speakers() == ["alice", "bob"]
+
+
+def test_voice_clone_prepends_ref_codes_and_cuts_proportionally():
+    core = _FakeCore()
+    core.tts_model_type = "base"
+    m = Qwen3TTSModel(core, _proc)
+    item = VoiceClonePromptItem(ref_code=torch.ones(6, 16, dtype=torch.long), ref_spk_embedding=torch.zeros(8),
+                                x_vector_only_mode=False, icl_mode=True, ref_text="ref")
+    wavs, fs = m.generate_voice_clone(["t1", "t2"], language="english", voice_clone_prompt=[item])
+    # decoded length (6+4)*1920, cut int(6/10*len) == 6*1920 (qwen3_tts_model.py:622-631)
+    assert [w.shape[0] for w in wavs] == [4 * 1920, 5 * 1920]
+    assert wavs[0][0] == 6 * 1920
+    kw = core.calls[-1]
+    assert kw["non_streaming_mode"] is False and len(kw["ref_ids"]) == 2 and kw["voice_clone_prompt"]["icl_mode"] == [True, True]
+    with pytest.raises(ValueError):
+        m.generate_voice_clone("t")
