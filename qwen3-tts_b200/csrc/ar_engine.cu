@@ -986,7 +986,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) q3_program_kernel(const __grid_co
       if (nx >= 0 && threadIdx.x < (int)(sizeof(Phase) / 4))
         reinterpret_cast<uint32_t*>(&s_ph[slot ^ 1])[threadIdx.x] = reinterpret_cast<const uint32_t*>(P.prog + nx)[threadIdx.x];
       const Phase& ph = s_ph[slot];
-      if (threadIdx.x == 0) g_prof_row = (P.prof && it == 0 && blockIdx.x == 0) ? P.prof + 8 * pi : nullptr;
+      if (threadIdx.x == 0) {
+        g_prof_row = (P.prof && it == 0) ? P.prof + ((size_t)pi * gridDim.x + blockIdx.x) * 8 : nullptr;
+        PROF_MARK(6);
+      }
       const int type = ph.type;
       if (type == PH_GEMV) gemv_phase<NT>(ph, P, smem, s_nw[slot]);
       else if (type == PH_ATTN) attn_phase(ph, P, smem, frame);
@@ -1004,20 +1007,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) q3_program_kernel(const __grid_co
           nw_have = true;
         }
       }
-      if (P.prof && it == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        P.prof[8 * pi] = t;
-      }
+      PROF_MARK(0);
       grid_barrier(st, epoch);
       slot ^= 1;
       if (nw_have) s_nw[slot][threadIdx.x] = nwv;  // visible to the next phase after its first __syncthreads... see below
       __syncthreads();
-      if (P.prof && it == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        P.prof[8 * pi + 1] = t;
-      }
+      PROF_MARK(1);
     }
     ++iters_done;
   }
@@ -1525,6 +1520,44 @@ extern "C" int q3_describe_frame_program(q3_engine* e, int32_t* kinds, int32_t c
     }
   }
   return -n;  // negative = count (0 is reserved for success elsewhere); callers use abs()
+}
+
+// Debug/profiling: run a synthetic program made of `count` repetitions of the frame-program phases
+// [first, first+span) (mode 0, one pass) and return the elapsed device time.  Used by tools/icache_probe.py.
+extern "C" int q3_debug_time_phases(q3_engine* e, int32_t first, int32_t span, int32_t count, float* ms_out, void* stream_) {
+  Q3_REQUIRE(e && e->prog_B > 0 && e->B > 0, "prefill first");
+  Q3_REQUIRE(first >= 0 && span >= 1 && first + span <= (int)e->prog_frame.size() && count >= 1, "bad phase range");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  std::vector<Phase> prog;
+  for (int i = 0; i < count; ++i)
+    for (int j = 0; j < span; ++j) {
+      Phase p = e->prog_frame[first + j];
+      if (p.type == PH_SAMPLE) continue;
+      prog.push_back(p);
+    }
+  const int n = (int)prog.size();
+  Phase* dev = nullptr;
+  Q3_CUDA(cudaMalloc(&dev, (size_t)n * sizeof(Phase)));
+  Q3_CUDA(cudaMemcpy(dev, prog.data(), (size_t)n * sizeof(Phase), cudaMemcpyHostToDevice));
+  Phase* saved = e->prog_dev;
+  e->prog_dev = dev;
+  const int B = e->B;
+  const int cols = (2 * B <= MAXCOLS) ? 2 * B : B;
+  const int nt = cols <= 8 ? 1 : cols <= 16 ? 2 : 4;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  int rc = launch_program(e, 0, n, 0, 1, nullptr, nt, nullptr, stream);  // warm
+  cudaEventRecord(e0, stream);
+  if (!rc) rc = launch_program(e, 0, n, 0, 1, nullptr, nt, nullptr, stream);
+  cudaEventRecord(e1, stream);
+  cudaStreamSynchronize(stream);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_out) *ms_out = ms;
+  e->prog_dev = saved;
+  cudaFree(dev);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return rc;
 }
 
 extern "C" int q3_algorithmic_bytes(q3_engine* e, int32_t B, int32_t S, double* a_bytes, double* a_stream_bytes) {

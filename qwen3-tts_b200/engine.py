@@ -173,13 +173,15 @@ class AREngine:
         n = -self.lib.q3_describe_frame_program(self.h, None, 0)
         kinds = (C.c_int32 * n)()
         self.lib.q3_describe_frame_program(self.h, kinds, n)
-        buf = torch.zeros(n, 8, dtype=torch.int64, device=self.device)
+        G = torch.cuda.get_device_properties(self.device).multi_processor_count
+        buf = torch.zeros(n, G, 8, dtype=torch.int64, device=self.device)
         _lib.check(self.lib.q3_set_profile(self.h, buf.data_ptr()))
         self.decode(max_frames, codes)
         torch.cuda.current_stream(self.device).synchronize()
         _lib.check(self.lib.q3_set_profile(self.h, None))
         t = buf.cpu().numpy()
-        return list(kinds), t[:, 0], t[:, 1], t[:, 2:6]
+        self.last_profile_all = t  # [phase][cta][8]: 0 end, 1 barrier passed, 2..5 inner marks, 6 start
+        return list(kinds), t[:, 0, 0], t[:, 0, 1], t[:, 0, 2:6]
 
     def algorithmic_bytes(self, B, S):
         a, s = C.c_double(), C.c_double()
