@@ -341,7 +341,7 @@ def main():
            "roofline": roof,
            "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "rtf": (e2e_ms / 1000.0) / (frames_total * FRAME_SEC)},
-           "gpu_launches": args.steps * (len(range(0, sum(lens), 32)) + 2 + eng.codec.last_launches()),
+           "gpu_launches": args.steps * (cfg.talker.num_layers * 8 + 2 + eng.codec.last_launches()),  # prefill (7 GEMM/row kernels + attention per layer) + head + fused decode + codec
            "clocks": clk}
 
     # ---- reference CPU path beside it (rank 0, N=1 only): bounded sample on the host cores

@@ -18,6 +18,7 @@
 //   * rounding points mirror the PyTorch bf16 path (linear outputs, RMSNorm, RoPE, residual adds are
 //     rounded to bf16 exactly where the reference rounds).
 #include "common.cuh"
+#include "gemm_sm100.cuh"
 #include "../../include/qwen3tts_b200.h"
 
 #include <cooperative_groups.h>
@@ -51,7 +52,7 @@ constexpr int XS_COL_BYTES = 4096 + 64;     // one staged column: K=2048 bf16 (+
 constexpr int XS_BYTES = 32 * XS_COL_BYTES;  // staged activations at NT=4: 32 cols
 // Shared memory is sized per batch class (NT n8-tiles): a small request leaves most of the 228 KB as L1, which is
 // what absorbs register spills / ABI stack traffic (with a 216 KB request every spill is an L2 round trip).
-constexpr int ATT_SMEM = (32 * 2 * 128 + 32 * 2 * 130) * 4;   // attention: qs + per-half-warp partials
+constexpr int ATT_SMEM = (2 * 2 * 128 + 32 * 2 * 130) * 4;    // attention: qs (<= 2 queries) + per-half-warp partials
 constexpr int SAMPLER_SMEM = (2 * 4096 + 64 + 256) * 4;
 __host__ __device__ constexpr int xs_bytes_nt(int nt) { return nt * 8 * XS_COL_BYTES; }
 __host__ __device__ constexpr int part_bytes_nt(int nt) { return 16 * 2 * nt * 8 * 20 * 4; }
@@ -62,8 +63,8 @@ constexpr int MAXV = 4096;       // max vocab handled by the sampler
 
 enum PhaseType { PH_GEMV = 0, PH_ATTN = 1, PH_SAMPLE = 2 };
 enum Epi { EPI_STORE = 0, EPI_BIAS = 1, EPI_RESID = 2, EPI_SWIGLU = 3, EPI_LOGITS = 4 };
-enum NcMode { NC_B = 0, NC_2B = 1, NC_CHUNK = 2 };
-enum SeqMode { SEQ_CP = 0, SEQ_DECODE = 1, SEQ_PREFILL = 2 };
+enum NcMode { NC_B = 0, NC_2B = 1 };
+enum SeqMode { SEQ_CP = 0, SEQ_DECODE = 1 };
 
 struct Phase {
   int type, epi, ncmode, stack;
@@ -113,11 +114,6 @@ struct DevState {
   unsigned int split_cnt[MAXB * 16];
 };
 
-struct ChunkDesc {  // prefill chunk (by value in the kernel parameters)
-  int nc, nseq;
-  int seq_id[MAXCOLS], q0[MAXCOLS], nq[MAXCOLS], ctx_end[MAXCOLS];
-};
-
 struct KParams {
   const Phase* prog;
   int n_phases;
@@ -147,8 +143,7 @@ struct KParams {
   int n_forced;
   float* dbg_tlogits;
   float* dbg_clogits;
-  unsigned long long* prof;  // [n_phases][8] globaltimer ns: [0] phase end, [1] barrier end, [2..5] inner marks (CTA 0)
-  ChunkDesc chunk;
+  unsigned long long* prof;  // [n_phases][grid][8] globaltimer ns: [0] phase end, [1] barrier passed, [2..5] inner marks, [6] start
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -226,7 +221,7 @@ __host__ __device__ __forceinline__ int xs_stride_bytes(int K) { return ((K * 2 
 
 __device__ __forceinline__ int phase_nc(int ncmode, const KParams& P) {
   const int B = P.B;
-  return ncmode == NC_B ? B : (ncmode == NC_2B ? 2 * B : P.chunk.nc);
+  return ncmode == NC_B ? B : 2 * B;
 }
 
 // balanced contiguous split of a phase's row tiles over the CTAs (tq/tr precomputed on the host)
@@ -495,7 +490,7 @@ __device__ __noinline__ void attn_phase(const Phase& ph, const KParams& P, unsig
   const int B = P.B;
   const int qkv_ld = (nh + 2 * nkv) * HD;
   const int seqmode = ph.seqmode, layer = ph.layer;
-  const int nseq = seqmode == SEQ_PREFILL ? P.chunk.nseq : B;
+  const int nseq = B;
   const float eps = S.eps;
   const bf16 *qn = ph.qn, *kn = ph.kn;
 
@@ -510,8 +505,8 @@ __device__ __noinline__ void attn_phase(const Phase& ph, const KParams& P, unsig
   }
   const int units = nseq * nkv * nsplit;
 
-  float* qs = reinterpret_cast<float*>(smem);                 // [nq<=32][RMAX][128]
-  float* red = qs + 32 * RMAX * HD;                           // [32 halfwarps][RMAX][130]
+  float* qs = reinterpret_cast<float*>(smem);                 // [nq<=2][RMAX][128]
+  float* red = qs + 2 * RMAX * HD;                            // [32 halfwarps][RMAX][130]
   __shared__ int s_ticket;
 
 #pragma unroll 1
@@ -521,8 +516,7 @@ __device__ __noinline__ void attn_phase(const Phase& ph, const KParams& P, unsig
     const int si = unit / (nsplit * nkv);
     int seq, q0, nq, qstride, ctx_end;
     if (seqmode == SEQ_CP) { seq = si; q0 = si; nq = ph.nq; qstride = B; ctx_end = ph.ctx_end; }
-    else if (seqmode == SEQ_DECODE) { seq = si; q0 = si; nq = 1; qstride = 0; ctx_end = P.len0[si] + frame + 1; }
-    else { seq = P.chunk.seq_id[si]; q0 = P.chunk.q0[si]; nq = P.chunk.nq[si]; qstride = 1; ctx_end = P.chunk.ctx_end[si]; }
+    else { seq = si; q0 = si; nq = 1; qstride = 0; ctx_end = P.len0[si] + frame + 1; }
     const int SL = (ctx_end + nsplit - 1) / nsplit;
     const int s0 = sp * SL, s1 = min(ctx_end, s0 + SL);
     bf16* kc = S.kc + (((size_t)seq * layers + layer) * nkv + kvh) * (size_t)cap * HD;
@@ -1020,6 +1014,118 @@ __global__ void __launch_bounds__(NTHREADS, 1) q3_program_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------
+// PREFILL on tensor cores: talker linears are tcgen05 tap-GEMMs (gemm_sm100.cu) over all prompt tokens at once
+// (M = sum of prompt lengths); the row-wise pieces around them are the small kernels below.
+// ------------------------------------------------------------------------------------------------
+__global__ void pf_rmsnorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y, int rows, int C,
+                                  float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (size_t)row * C);
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  float ss = 0.f;
+  for (int i = lane; i < C / 8; i += 32) {
+    const uint4 v = xr[i];
+    float f;
+    f = bf16lo(v.x); ss += f * f; f = bf16hi(v.x); ss += f * f;
+    f = bf16lo(v.y); ss += f * f; f = bf16hi(v.y); ss += f * f;
+    f = bf16lo(v.z); ss += f * f; f = bf16hi(v.z); ss += f * f;
+    f = bf16lo(v.w); ss += f * f; f = bf16hi(v.w); ss += f * f;
+  }
+  ss = warp_sum(ss);
+  const float inv = rsqrtf(ss / (float)C + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y + (size_t)row * C);
+  for (int i = lane; i < C / 8; i += 32) {
+    const uint4 v = xr[i], wv = wr[i];
+    uint4 o;
+    o.x = pack_bf16(rbf(bf16lo(v.x) * inv) * bf16lo(wv.x), rbf(bf16hi(v.x) * inv) * bf16hi(wv.x));
+    o.y = pack_bf16(rbf(bf16lo(v.y) * inv) * bf16lo(wv.y), rbf(bf16hi(v.y) * inv) * bf16hi(wv.y));
+    o.z = pack_bf16(rbf(bf16lo(v.z) * inv) * bf16lo(wv.z), rbf(bf16hi(v.z) * inv) * bf16hi(wv.z));
+    o.w = pack_bf16(rbf(bf16lo(v.w) * inv) * bf16lo(wv.w), rbf(bf16hi(v.w) * inv) * bf16hi(wv.w));
+    yr[i] = o;
+  }
+}
+
+// per (token, head-vector): q heads RMSNorm+RoPE in place; k head -> K cache (normed, roped); v head -> V cache
+__global__ void pf_qkv_post_kernel(bf16* __restrict__ qkv, int ntok, const int* __restrict__ tok_seq, const int* __restrict__ tok_pos,
+                                   int nh, int nkv, const bf16* __restrict__ qn, const bf16* __restrict__ kn, float eps,
+                                   const bf16* __restrict__ cosT, const bf16* __restrict__ sinT, bf16* __restrict__ kc,
+                                   bf16* __restrict__ vc, int layer, int layers, int cap) {
+  const int nvec = nh + 2 * nkv;
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= ntok * nvec) return;
+  const int lane = threadIdx.x & 31;
+  const int tok = wid / nvec, v = wid - tok * nvec;
+  const int seq = tok_seq[tok], pos = tok_pos[tok];
+  bf16* src = qkv + (size_t)tok * (size_t)(nvec * HD) + (size_t)v * HD;
+  const bf16* cosr = cosT + (size_t)pos * 64;
+  const bf16* sinr = sinT + (size_t)pos * 64;
+  if (v < nh) {
+    norm_rope_vec(src, qn, eps, cosr, sinr, nullptr, src);
+  } else if (v < nh + nkv) {
+    const int kvh = v - nh;
+    norm_rope_vec(src, kn, eps, cosr, sinr, nullptr, kc + ((((size_t)seq * layers + layer) * nkv + kvh) * cap + pos) * HD);
+  } else {
+    const int kvh = v - nh - nkv;
+    bf16* d = vc + ((((size_t)seq * layers + layer) * nkv + kvh) * cap + pos) * HD;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[lane + 32 * i] = src[lane + 32 * i];
+  }
+}
+
+// causal attention over the KV cache, one warp per (token, q head); keys in blocks of 32 with an online softmax
+__global__ void pf_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ attn, int ntok, const int* __restrict__ tok_seq,
+                                    const int* __restrict__ tok_pos, int nh, int nkv, const bf16* __restrict__ kc,
+                                    const bf16* __restrict__ vc, int layer, int layers, int cap) {
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= ntok * nh) return;
+  const int lane = threadIdx.x & 31;
+  const int tok = wid / nh, h = wid - tok * nh;
+  const int seq = tok_seq[tok], pos = tok_pos[tok];
+  const int kvh = h / (nh / nkv);
+  const bf16* q = qkv + (size_t)tok * (size_t)((nh + 2 * nkv) * HD) + (size_t)h * HD;
+  const bf16* K = kc + (((size_t)seq * layers + layer) * nkv + kvh) * (size_t)cap * HD;
+  const bf16* V = vc + (((size_t)seq * layers + layer) * nkv + kvh) * (size_t)cap * HD;
+  const float scale = rsqrtf((float)HD);
+  float m = -INFINITY, l = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int kb = 0; kb <= pos; kb += 32) {
+    const int key = kb + lane;
+    float sc = -INFINITY;
+    if (key <= pos) {
+      const uint4* kr = reinterpret_cast<const uint4*>(K + (size_t)key * HD);
+      const uint4* qr = reinterpret_cast<const uint4*>(q);
+      float d = 0.f;
+#pragma unroll 4
+      for (int i = 0; i < HD / 8; ++i) {
+        const uint4 a = qr[i], b = kr[i];
+        d += bf16lo(a.x) * bf16lo(b.x) + bf16hi(a.x) * bf16hi(b.x) + bf16lo(a.y) * bf16lo(b.y) + bf16hi(a.y) * bf16hi(b.y) +
+             bf16lo(a.z) * bf16lo(b.z) + bf16hi(a.z) * bf16hi(b.z) + bf16lo(a.w) * bf16lo(b.w) + bf16hi(a.w) * bf16hi(b.w);
+      }
+      sc = d * scale;
+    }
+    const float mn = fmaxf(m, warp_max(sc));
+    const float corr = __expf(m - mn);
+    const float p = (key <= pos) ? __expf(sc - mn) : 0.f;
+    l = l * corr + warp_sum(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] *= corr;
+    const int nk = min(32, pos - kb + 1);
+    for (int j = 0; j < nk; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, p, j);
+      const uint2 vv = *reinterpret_cast<const uint2*>(V + (size_t)(kb + j) * HD + lane * 4);
+      o[0] += pj * bf16lo(vv.x); o[1] += pj * bf16hi(vv.x); o[2] += pj * bf16lo(vv.y); o[3] += pj * bf16hi(vv.y);
+    }
+    m = mn;
+  }
+  const float inv = 1.f / l;
+  uint2 r;
+  r.x = pack_bf16(o[0] * inv, o[1] * inv);
+  r.y = pack_bf16(o[2] * inv, o[3] * inv);
+  *reinterpret_cast<uint2*>(attn + (size_t)tok * (size_t)(nh * HD) + (size_t)h * HD + lane * 4) = r;
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight packing: row-major [N][K] bf16 -> stream of (16 rows x 32 k) 1 KB blocks, each two 8x32 halves
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_weight_kernel(const bf16* __restrict__ src, uint4* __restrict__ dst, int N, int K) {
@@ -1052,6 +1158,10 @@ struct q3_engine {
   int sm_count = 0;
   cudaStream_t copy_stream = nullptr;
   std::map<std::string, PackedW> packed;   // GEMV weights
+  std::map<std::string, bf16*> gemm_w;      // plain [N][K] copies of the talker layer weights for the tcgen05 prefill GEMMs
+  bf16 *pf_x = nullptr, *pf_xn = nullptr, *pf_qkv = nullptr, *pf_attn = nullptr, *pf_act = nullptr;
+  int *pf_seq = nullptr, *pf_pos = nullptr;
+  int pf_cap = 0;
   std::map<std::string, bf16*> plain;      // norms, biases, embeddings, rope tables
   std::map<std::string, std::pair<int64_t, int64_t>> plain_shape;
   std::vector<void*> allocs;
@@ -1136,6 +1246,7 @@ extern "C" int q3_engine_create(const q3_engine_cfg* cfg, q3_engine** out) {
   e->cfg = *cfg;
   e->sm_count = prop.multiProcessorCount;
   Q3_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+  if (gemm_init()) return 1;
   if (e->alloc(&e->st, 1)) return 1;
   if (stack_alloc(e, e->talker, cfg->talker, cfg->max_batch, cfg->max_ctx, MAXCOLS)) return 1;
   if (stack_alloc(e, e->cp, cfg->cp, cfg->max_batch, 32, MAXCOLS)) return 1;
@@ -1182,6 +1293,14 @@ extern "C" int q3_engine_load_tensor(q3_engine* e, const char* name, const void*
     Q3_CUDA(cudaGetLastError());
     Q3_CUDA(cudaStreamSynchronize(e->copy_stream));
     e->packed[n] = pw;
+    if (n.rfind("talker.layers.", 0) == 0) {  // prefill GEMM operand: the source layout [N][K] is already K-major
+      Q3_REQUIRE(cols % 64 == 0, "%s: K must be a multiple of 64 for the prefill GEMM", name);
+      bf16* g = nullptr;
+      if (e->alloc(&g, (size_t)rows * cols)) return 1;
+      Q3_CUDA(cudaMemcpyAsync(g, dev, (size_t)rows * cols * sizeof(bf16), cudaMemcpyDeviceToDevice, e->copy_stream));
+      Q3_CUDA(cudaStreamSynchronize(e->copy_stream));
+      e->gemm_w[n] = g;
+    }
   } else {
     bf16* p = nullptr;
     if (e->alloc(&p, (size_t)rows * cols)) return 1;
@@ -1262,8 +1381,7 @@ static int build_programs(q3_engine* e, int B) {
     if (need_packed(e, "cp.proj", Hc, H, &wproj) || need_plain(e, "cp.proj_bias", Hc, &bproj)) return 1;
   }
   // ---- prefill-chunk program: talker layers over the chunk's columns
-  e->prog_layers.clear();
-  if (add_layers(e, e->prog_layers, "talker", T, T.h, NC_CHUNK, SEQ_PREFILL, 0, 0)) return 1;
+  e->prog_layers.clear();  // (prefill runs on the tcgen05 GEMM path, see q3_prefill)
   // ---- prefill-head program: final norm + codec_head on the last token of each row, sample frame-0 codebook-0
   e->prog_head.clear();
   {
@@ -1373,7 +1491,7 @@ extern "C" int q3_engine_finalize(q3_engine* e) {
   return 0;
 }
 
-static int launch_program(q3_engine* e, int off, int n, int mode, int max_iters, const ChunkDesc* chunk, int nt,
+static int launch_program(q3_engine* e, int off, int n, int mode, int max_iters, int nt,
                           int* codes_dev, cudaStream_t stream) {
   KParams P{};
   P.prog = e->prog_dev + off; P.n_phases = n; P.mode = mode; P.max_iters = max_iters; P.st = e->st;
@@ -1385,7 +1503,6 @@ static int launch_program(q3_engine* e, int off, int n, int mode, int max_iters,
   P.x_cp = e->cfg.has_cp_projection ? e->x_cp : e->cp.h; P.past_hidden = e->past_hidden; P.trailing = e->trailing; P.trailing_stride = e->trailing_cap;
   P.tts_pad = e->tts_pad; P.seen = e->seen; P.codes_out = codes_dev; P.codes_stride = e->codes_stride;
   P.split_buf = e->split_buf; P.forced = e->forced; P.n_forced = e->n_forced; P.dbg_tlogits = e->dbg_t; P.dbg_clogits = e->dbg_c; P.prof = (mode == 1) ? e->prof : nullptr;
-  if (chunk) P.chunk = *chunk;
   Q3_CUDA(cudaMemsetAsync(&e->st->bar_count, 0, sizeof(unsigned int), stream));
   void* args[] = {&P};
   const void* fn = nt == 1 ? (const void*)q3_program_kernel<1> : nt == 2 ? (const void*)q3_program_kernel<2>
@@ -1432,33 +1549,61 @@ extern "C" int q3_prefill(q3_engine* e, int32_t B, const void* embeds_dev, const
   e->trailing_cap = trailing_stride;
   e->codes_stride = 0;
   e->frames_issued = 0;
-  // chunked prefill: <= MAXCOLS prompt tokens per pass, sequences packed back to back
-  int total = 0;
-  std::vector<int> start(B);
-  for (int b = 0; b < B; ++b) { start[b] = total; total += lens_host[b]; }
-  for (int r0 = 0; r0 < total; r0 += MAXCOLS) {
-    const int r1 = std::min(total, r0 + MAXCOLS);
-    ChunkDesc ch;
-    memset(&ch, 0, sizeof(ch));
-    ch.nc = r1 - r0;
-    for (int b = 0; b < B; ++b) {
-      const int a = std::max(r0, start[b]), z = std::min(r1, start[b] + lens_host[b]);
-      if (z <= a) continue;
-      const int i = ch.nseq++;
-      ch.seq_id[i] = b; ch.q0[i] = a - r0; ch.nq[i] = z - a; ch.ctx_end[i] = z - start[b];
-    }
-    Q3_CUDA(cudaMemcpyAsync(e->talker.h, reinterpret_cast<const bf16*>(embeds_dev) + (size_t)r0 * H,
-                            (size_t)ch.nc * H * 2, cudaMemcpyDeviceToDevice, stream));
-    if (launch_program(e, e->off_layers, (int)e->prog_layers.size(), 0, 1, &ch, 4, nullptr, stream)) return 1;
-    for (int i = 0; i < ch.nseq; ++i) {
-      const int b = ch.seq_id[i];
-      if (ch.ctx_end[i] == lens_host[b])  // last prompt token of row b lives in this chunk
-        Q3_CUDA(cudaMemcpyAsync(e->h_last + (size_t)b * H, e->talker.h + (size_t)(ch.q0[i] + ch.nq[i] - 1) * H,
-                                (size_t)H * 2, cudaMemcpyDeviceToDevice, stream));
-    }
+  // ---- prefill on tensor cores: all prompt tokens of all rows at once (packed [ntok][H], rows back to back)
+  int ntok = 0;
+  std::vector<int> hseq, hpos, last(B);
+  for (int b = 0; b < B; ++b) {
+    for (int p = 0; p < lens_host[b]; ++p) { hseq.push_back(b); hpos.push_back(p); }
+    ntok += lens_host[b];
+    last[b] = ntok - 1;
   }
+  const q3_stack_cfg& tc = e->cfg.talker;
+  const int nh = tc.num_heads, nkv = tc.num_kv_heads, I = tc.intermediate_size, QKV = (nh + 2 * nkv) * HD;
+  if (ntok > e->pf_cap) {
+    const int cap = std::max(ntok, 1024);
+    if (e->alloc(&e->pf_x, (size_t)cap * H) || e->alloc(&e->pf_xn, (size_t)cap * H) || e->alloc(&e->pf_qkv, (size_t)cap * QKV) ||
+        e->alloc(&e->pf_attn, (size_t)cap * nh * HD) || e->alloc(&e->pf_act, (size_t)cap * I) || e->alloc(&e->pf_seq, (size_t)cap) ||
+        e->alloc(&e->pf_pos, (size_t)cap))
+      return 1;
+    e->pf_cap = cap;
+  }
+  Q3_CUDA(cudaMemcpyAsync(e->pf_seq, hseq.data(), (size_t)ntok * sizeof(int), cudaMemcpyHostToDevice, stream));
+  Q3_CUDA(cudaMemcpyAsync(e->pf_pos, hpos.data(), (size_t)ntok * sizeof(int), cudaMemcpyHostToDevice, stream));
+  Q3_CUDA(cudaStreamSynchronize(stream));  // hseq/hpos are stack-owned pageable buffers
+  Q3_CUDA(cudaMemcpyAsync(e->pf_x, embeds_dev, (size_t)ntok * H * 2, cudaMemcpyDeviceToDevice, stream));
+  const int mt = (ntok + 127) / 128;
+  const int zero = 0;
+  auto gemm = [&](const bf16* a, int K, const std::string& wname, int N, GemmEpilogue ep) -> int {
+    auto it = e->gemm_w.find(wname);
+    Q3_REQUIRE(it != e->gemm_w.end(), "missing prefill GEMM weight %s", wname.c_str());
+    ep.cmod = N;
+    GemmPlan plan;
+    if (gemm_make_plan(&plan, a, 1, ntok, K, K, (int64_t)ntok * K, it->second, N, K, 1, &zero, gemm_pick_bn(N, mt, 1), ep)) return 1;
+    return gemm_launch(plan, stream);
+  };
+  const int rows_per_blk = 8;
+  for (int l = 0; l < tc.num_layers; ++l) {
+    const std::string p = "talker.layers." + std::to_string(l);
+    const bf16 *ln1 = e->plain[p + ".ln1"], *ln2 = e->plain[p + ".ln2"], *qn = e->plain[p + ".q_norm"], *kn = e->plain[p + ".k_norm"];
+    Q3_REQUIRE(ln1 && ln2 && qn && kn, "missing norm weights of %s", p.c_str());
+    pf_rmsnorm_kernel<<<(ntok + rows_per_blk - 1) / rows_per_blk, 256, 0, stream>>>(e->pf_x, ln1, e->pf_xn, ntok, H, tc.rms_eps);
+    { GemmEpilogue ep{}; ep.out_raw = e->pf_qkv; if (gemm(e->pf_xn, H, p + ".qkv", QKV, ep)) return 1; }
+    pf_qkv_post_kernel<<<(ntok * (nh + 2 * nkv) + 7) / 8, 256, 0, stream>>>(e->pf_qkv, ntok, e->pf_seq, e->pf_pos, nh, nkv, qn, kn, tc.rms_eps,
+                                                                         e->talker.rope_cos, e->talker.rope_sin, e->talker.kc,
+                                                                         e->talker.vc, l, tc.num_layers, e->talker.cap);
+    pf_attention_kernel<<<(ntok * nh + 7) / 8, 256, 0, stream>>>(e->pf_qkv, e->pf_attn, ntok, e->pf_seq, e->pf_pos, nh, nkv, e->talker.kc,
+                                                                 e->talker.vc, l, tc.num_layers, e->talker.cap);
+    { GemmEpilogue ep{}; ep.resid = e->pf_x; ep.out_raw = e->pf_x; if (gemm(e->pf_attn, nh * HD, p + ".o", H, ep)) return 1; }
+    pf_rmsnorm_kernel<<<(ntok + rows_per_blk - 1) / rows_per_blk, 256, 0, stream>>>(e->pf_x, ln2, e->pf_xn, ntok, H, tc.rms_eps);
+    { GemmEpilogue ep{}; ep.act = ACT_SWIGLU_BLK8; ep.out_act = e->pf_act; if (gemm(e->pf_xn, H, p + ".gate_up", 2 * I, ep)) return 1; }
+    { GemmEpilogue ep{}; ep.resid = e->pf_x; ep.out_raw = e->pf_x; if (gemm(e->pf_act, I, p + ".down", H, ep)) return 1; }
+  }
+  Q3_CUDA(cudaGetLastError());
+  for (int b = 0; b < B; ++b)
+    Q3_CUDA(cudaMemcpyAsync(e->h_last + (size_t)b * H, e->pf_x + (size_t)last[b] * H, (size_t)H * 2, cudaMemcpyDeviceToDevice, stream));
   // head + sample codebook-0 of frame 0 (codes are materialised by q3_decode's first call via st->c0)
-  if (launch_program(e, e->off_head, (int)e->prog_head.size(), 0, 1, nullptr, 4, nullptr, stream)) return 1;
+  const int nt_head = B <= 8 ? 1 : B <= 16 ? 2 : 4;
+  if (launch_program(e, e->off_head, (int)e->prog_head.size(), 0, 1, nt_head, nullptr, stream)) return 1;
   return 0;
 }
 
@@ -1474,7 +1619,7 @@ extern "C" int q3_decode(q3_engine* e, int32_t max_frames, int32_t* codes_dev, i
   const int B = e->B;
   const int cols = (2 * B <= MAXCOLS) ? 2 * B : B;
   const int nt = cols <= 8 ? 1 : cols <= 16 ? 2 : 4;
-  return launch_program(e, e->off_frame, (int)e->prog_frame.size(), 1, max_frames, nullptr, nt, codes_dev, stream);
+  return launch_program(e, e->off_frame, (int)e->prog_frame.size(), 1, max_frames, nt, codes_dev, stream);
 }
 
 extern "C" int q3_get_progress(q3_engine* e, int32_t* frames_done, int32_t* n_valid, int32_t* finished) {
@@ -1546,9 +1691,9 @@ extern "C" int q3_debug_time_phases(q3_engine* e, int32_t first, int32_t span, i
   const int nt = cols <= 8 ? 1 : cols <= 16 ? 2 : 4;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  int rc = launch_program(e, 0, n, 0, 1, nullptr, nt, nullptr, stream);  // warm
+  int rc = launch_program(e, 0, n, 0, 1, nt, nullptr, stream);  // warm
   cudaEventRecord(e0, stream);
-  if (!rc) rc = launch_program(e, 0, n, 0, 1, nullptr, nt, nullptr, stream);
+  if (!rc) rc = launch_program(e, 0, n, 0, 1, nt, nullptr, stream);
   cudaEventRecord(e1, stream);
   cudaStreamSynchronize(stream);
   float ms = 0.f;

@@ -293,19 +293,6 @@ struct Runner {
   int B;
   int err = 0;
 
-  static int pick_bn(int N, int mtiles, int B) {
-    static const int cand[] = {256, 240, 224, 208, 192, 176, 160, 144, 128, 112, 96, 80, 64};
-    int best_small = 0;
-    for (int bn : cand) {
-      if (N % bn) continue;
-      if ((long long)mtiles * (N / bn) * B >= 148) return bn;
-      best_small = bn;
-    }
-    if (best_small) return best_small;
-    for (int bn : cand) if (bn <= N) return bn;
-    return N;  // N < 64 (multiple of 16)
-  }
-
   // one tap-GEMM: a [B][T][K] -> [B][T][N]
   void gemm(const bf16* a, int T, int K, const char* wname, int N, int ntaps, const int* shifts, GemmEpilogue ep) {
     if (err) return;
@@ -319,7 +306,7 @@ struct Runner {
     GemmPlan plan;
     const int mt = (T + 127) / 128;
     if (gemm_make_plan(&plan, a, B, T, K, K, (int64_t)T * K, reinterpret_cast<const bf16*>(w->p), N, Kp, ntaps, shifts,
-                       pick_bn(N, mt, B), ep)) { err = 1; return; }
+                       gemm_pick_bn(N, mt, B), ep)) { err = 1; return; }
     if (gemm_launch(plan, stream)) { err = 1; return; }
     c->launches++;
   }

@@ -187,7 +187,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
         *reinterpret_cast<uint4*>(E.out_raw + row_off + n + 8) = o1;
       }
       if (E.out_act) {
-        if (E.act == ACT_SWIGLU_PAIR) {
+        if (E.act == ACT_SWIGLU_BLK8) {
+          // 16 columns = gate[8j..8j+7] | up[8j..8j+7] (the AR engine's gate_up row interleave); out is [..][N/2]
+          float y[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float g = x[i], u = x[8 + i];
+            y[i] = rbf(g / (1.f + __expf(-g))) * u;
+          }
+          uint4 o;
+          o.x = pack_bf16(y[0], y[1]); o.y = pack_bf16(y[2], y[3]); o.z = pack_bf16(y[4], y[5]); o.w = pack_bf16(y[6], y[7]);
+          *reinterpret_cast<uint4*>(E.out_act + ((size_t)b * p.T + m) * (size_t)(p.N / 2) + n / 2) = o;
+        } else if (E.act == ACT_SWIGLU_PAIR) {
           // columns (2i, 2i+1) = (gate_i, up_i)
           float y[8];
 #pragma unroll
@@ -281,6 +292,20 @@ int gemm_make_plan(GemmPlan* plan, const bf16* a, int B, int T, int K, int64_t l
     Q3_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(W) failed: %d (N=%d Kp=%d taps=%d)", (int)r, N, Kp, ntaps);
   }
   return 0;
+}
+
+int gemm_pick_bn(int N, int mtiles, int B) {
+  static const int cand[] = {256, 240, 224, 208, 192, 176, 160, 144, 128, 112, 96, 80, 64};
+  int best_small = 0;
+  for (int bn : cand) {
+    if (N % bn) continue;
+    if ((long long)mtiles * (N / bn) * B >= 148) return bn;
+    best_small = bn;
+  }
+  if (best_small) return best_small;
+  for (int bn : cand)
+    if (bn <= N) return bn;
+  return N;  // N < 64 (multiple of 16)
 }
 
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {

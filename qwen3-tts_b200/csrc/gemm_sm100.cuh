@@ -9,7 +9,7 @@
 #include <stdint.h>
 #include "common.cuh"
 
-enum GemmAct { ACT_NONE = 0, ACT_SNAKE = 1, ACT_GELU = 2, ACT_SWIGLU_PAIR = 3 };
+enum GemmAct { ACT_NONE = 0, ACT_SNAKE = 1, ACT_GELU = 2, ACT_SWIGLU_PAIR = 3, ACT_SWIGLU_BLK8 = 4 };
 
 struct GemmEpilogue {
   const float* bias;      // [cmod] or null; channel = n % cmod
@@ -36,3 +36,4 @@ int gemm_make_plan(GemmPlan* plan, const bf16* a, int B, int T, int K, int64_t l
                    const bf16* w, int N, int Kp, int ntaps, const int* shifts, int bn, const GemmEpilogue& ep);
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
 int gemm_init();  // resolves cuTensorMapEncodeTiled, sets kernel attributes
+int gemm_pick_bn(int N, int mtiles, int B);  // largest tile width that still fills the 148 SMs
