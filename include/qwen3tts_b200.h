@@ -119,6 +119,7 @@ int q3_set_debug(q3_engine* e, const int32_t* forced_dev, int32_t n_frames, floa
 int q3_set_profile(q3_engine* e, unsigned long long* prof_dev);
 int q3_describe_frame_program(q3_engine* e, int32_t* kinds, int32_t capacity);
 /* time `count` repetitions of frame-program phases [first, first+span) as one launch (instruction-cache probe) */
+int q3_debug_set_skip(q3_engine* e, int32_t mask); /* ablation bits for tools/ablate_phase.py; 0 = normal */
 int q3_debug_time_phases(q3_engine* e, int32_t first, int32_t span, int32_t count, float* ms_out, void* stream);
 
 /* Bytes the fused frame-step kernel must stream per step for batch B at mean context S

@@ -23,6 +23,7 @@
 
 #include <cooperative_groups.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <map>
 #include <vector>
@@ -143,6 +144,7 @@ struct KParams {
   int n_forced;
   float* dbg_tlogits;
   float* dbg_clogits;
+  int dbg_skip;             // ablation bits (tools/ablate_phase.py): 1 stage, 2 main loop, 4 epilogue, 8 preload, 16 whole body
   unsigned long long* prof;  // [n_phases][grid][8] globaltimer ns: [0] phase end, [1] barrier passed, [2..5] inner marks, [6] start
 };
 
@@ -157,7 +159,12 @@ __device__ __forceinline__ void grid_barrier(DevState* st, unsigned int& epoch) 
     long long t0 = clock64();
     unsigned int v;
     while (true) {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&st->bar_count) : "memory");
+      // RELAXED poll on purpose: ld.acquire.gpu compiles to LDG.STRONG + CCTL.IVALL, i.e. it invalidates the whole
+      // L1 on every poll iteration (measured: ~55 invalidations per barrier), which evicts the stack / spill lines
+      // of all 16 warps and makes every phase start cold.  Correctness does not need the invalidation: every
+      // cross-CTA read in this kernel is an L2 load (ld.global.cg), the writers released at gpu scope before
+      // their arrival became visible, and the GPU does not speculate loads past this loop + bar.sync.
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&st->bar_count) : "memory");
       if ((int)(v - epoch) >= 0) break;
       if (clock64() - t0 > 8000000000LL) {  // ~4 s: never hang the box
         st->error = 77;
@@ -166,7 +173,7 @@ __device__ __forceinline__ void grid_barrier(DevState* st, unsigned int& epoch) 
       }
     }
   }
-  __syncthreads();  // cross-CTA data is always read with ld.global.cg (L2), so no L1 invalidation is needed here
+  __syncthreads();
 }
 
 // fine-grained profiling marks (thread 0 of CTA 0 only, first frame of a profiled launch)
@@ -355,6 +362,8 @@ __device__ __noinline__ void gemv_phase(const Phase& ph, const KParams& P, unsig
   const int nc = phase_nc(ph.ncmode, P);
   int t0, ntc;
   cta_tiles(ph.tq, ph.tr, t0, ntc);
+  const int skip = P.dbg_skip;
+  if (skip & 16) return;
 
   char* xs = reinterpret_cast<char*>(smem);
   float* part = reinterpret_cast<float*>(smem + xs_bytes_nt(NT));  // [NWARPS][2][NT*8][PCOL]
@@ -365,13 +374,13 @@ __device__ __noinline__ void gemv_phase(const Phase& ph, const KParams& P, unsig
   uint4 afr[DEPTH][2];
   const int TB0 = min(NWARPS, ntc);
   const int upw0 = (TB0 * KB + NWARPS - 1) / NWARPS;
-  const bool have0 = ntc > 0 && warp * upw0 < TB0 * KB;
+  const bool have0 = ntc > 0 && warp * upw0 < TB0 * KB && !(skip & (8 | 2));
   if (have0) {
     const int u = warp * upw0, tl = u / KB, kb0 = u - tl * KB;
     gemv_preload(afr, wbase + ((size_t)(t0 + tl) * KB + kb0) * 64 + lane, min(KB - kb0, min(TB0 * KB, u + upw0) - u));
   }
   PROF_MARK(2);
-  if (staged && (ntc > 0 || save)) stage_columns(src, src_ld, norm_w != nullptr, ph.eps, save, K, nc, xs, xstride, nw_s);
+  if (staged && (ntc > 0 || save) && !(skip & 1)) stage_columns(src, src_ld, norm_w != nullptr, ph.eps, save, K, nc, xs, xstride, nw_s);
   __syncthreads();
   PROF_MARK(3);
   if (ntc <= 0) return;
@@ -392,9 +401,11 @@ __device__ __noinline__ void gemv_phase(const Phase& ph, const KParams& P, unsig
 #pragma unroll
       for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
       const uint4* wp = wbase + ((size_t)(t0 + tb0 + tl) * KB + kb0) * 64 + lane;
-      if (!(tb0 == 0 && seg == 0)) gemv_preload(afr, wp, nk);  // the very first segment was preloaded above
+      if (!(skip & 2)) {
+      if (!(tb0 == 0 && seg == 0) || (skip & 8)) gemv_preload(afr, wp, nk);  // the very first segment was preloaded above
       if (staged) gemv_segment<NT, true>(acc, afr, wp, nk, kb0, xs, xstride, src, src_ld, nc, g, t);
       else gemv_segment<NT, false>(acc, afr, wp, nk, kb0, xs, xstride, src, src_ld, nc, g, t);
+      }
       // spill partial sums: part[warp][seg][col][row]
       float* pp = part + ((warp * 2 + seg) * (NT * 8)) * PCOL;
 #pragma unroll
@@ -413,7 +424,7 @@ __device__ __noinline__ void gemv_phase(const Phase& ph, const KParams& P, unsig
     // ---- cross-warp reduce + epilogue, one element per thread-iteration (independent global round trips)
     const bool swiglu = epi == EPI_SWIGLU;
     const int rsh = swiglu ? 3 : 4;  // rows per tile: 8 (gate/up pairs) or 16
-    const int nelem = (TB << rsh) * nc;
+    const int nelem = (skip & 4) ? 0 : (TB << rsh) * nc;
 #pragma unroll 1
     for (int e = tid; e < nelem; e += NTHREADS) {
       const int r = e & ((1 << rsh) - 1);
@@ -974,11 +985,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) q3_program_kernel(const __grid_co
     }
 #pragma unroll 1
     for (int pi = 0; pi < P.n_phases; ++pi) {
-      // descriptor pi sits in s_ph[pi & 1] (fetched one phase ahead); fetch pi+1 now, it lands during this phase
+      // descriptor of this phase sits in s_ph[slot] (fetched one phase ahead).  The load of the NEXT descriptor is
+      // issued now into a register and only stored to smem after the body, so its L2 round trip is hidden.
       int nx = pi + 1;
       if (nx >= P.n_phases) nx = (P.mode == 1) ? 0 : -1;
-      if (nx >= 0 && threadIdx.x < (int)(sizeof(Phase) / 4))
-        reinterpret_cast<uint32_t*>(&s_ph[slot ^ 1])[threadIdx.x] = reinterpret_cast<const uint32_t*>(P.prog + nx)[threadIdx.x];
+      const bool dhave = nx >= 0 && threadIdx.x < (int)(sizeof(Phase) / 4);
+      uint32_t dreg = 0;
+      if (dhave) dreg = reinterpret_cast<const uint32_t*>(P.prog + nx)[threadIdx.x];
       const Phase& ph = s_ph[slot];
       if (threadIdx.x == 0) {
         g_prof_row = (P.prof && it == 0) ? P.prof + ((size_t)pi * gridDim.x + blockIdx.x) * 8 : nullptr;
@@ -988,6 +1001,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) q3_program_kernel(const __grid_co
       if (type == PH_GEMV) gemv_phase<NT>(ph, P, smem, s_nw[slot]);
       else if (type == PH_ATTN) attn_phase(ph, P, smem, frame);
       else sample_phase(ph, P, smem, frame, P.mode == 0);
+      if (dhave) reinterpret_cast<uint32_t*>(&s_ph[slot ^ 1])[threadIdx.x] = dreg;
       __syncthreads();
       // pull the next GEMV's weight slice toward L2 while the barrier drains, and fetch its norm weights (the
       // load is issued before the barrier, the smem store happens after it: zero exposed latency)
@@ -995,8 +1009,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) q3_program_kernel(const __grid_co
       bool nw_have = false;
       if (nx >= 0) {
         const Phase& nph = s_ph[slot ^ 1];
-        prefetch_phase_weights(nph);
-        if (nph.type == PH_GEMV && nph.norm_w != nullptr && (int)threadIdx.x < nph.kb * 4) {
+        if (!(P.dbg_skip & 32)) prefetch_phase_weights(nph);
+        if (!(P.dbg_skip & 64) && nph.type == PH_GEMV && nph.norm_w != nullptr && (int)threadIdx.x < nph.kb * 4) {
           nwv = reinterpret_cast<const uint4*>(nph.norm_w)[threadIdx.x];
           nw_have = true;
         }
@@ -1180,6 +1194,7 @@ struct q3_engine {
   int prog_cap = 0;
   // programs (host copies) for the current batch size
   int prog_B = -1;
+  int dbg_skip = 0;
   std::vector<Phase> prog_layers, prog_head, prog_frame;
   int off_layers = 0, off_head = 0, off_frame = 0;
   q3_sampling sp{};
@@ -1245,6 +1260,10 @@ extern "C" int q3_engine_create(const q3_engine_cfg* cfg, q3_engine** out) {
   q3_engine* e = new q3_engine();
   e->cfg = *cfg;
   e->sm_count = prop.multiProcessorCount;
+  if (const char* g = getenv("Q3_GRID")) {  // experiment knob: persistent grid smaller than the SM count
+    const int v = atoi(g);
+    if (v >= 8 && v <= e->sm_count) e->sm_count = v;
+  }
   Q3_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   if (gemm_init()) return 1;
   if (e->alloc(&e->st, 1)) return 1;
@@ -1502,7 +1521,7 @@ static int launch_program(q3_engine* e, int off, int n, int mode, int max_iters,
   P.emb_t = e->plain["talker.codec_embedding"]; P.emb_cp = e->plain["cp.codec_embedding"];
   P.x_cp = e->cfg.has_cp_projection ? e->x_cp : e->cp.h; P.past_hidden = e->past_hidden; P.trailing = e->trailing; P.trailing_stride = e->trailing_cap;
   P.tts_pad = e->tts_pad; P.seen = e->seen; P.codes_out = codes_dev; P.codes_stride = e->codes_stride;
-  P.split_buf = e->split_buf; P.forced = e->forced; P.n_forced = e->n_forced; P.dbg_tlogits = e->dbg_t; P.dbg_clogits = e->dbg_c; P.prof = (mode == 1) ? e->prof : nullptr;
+  P.split_buf = e->split_buf; P.forced = e->forced; P.n_forced = e->n_forced; P.dbg_tlogits = e->dbg_t; P.dbg_clogits = e->dbg_c; P.prof = (mode == 1) ? e->prof : nullptr; P.dbg_skip = e->dbg_skip;
   Q3_CUDA(cudaMemsetAsync(&e->st->bar_count, 0, sizeof(unsigned int), stream));
   void* args[] = {&P};
   const void* fn = nt == 1 ? (const void*)q3_program_kernel<1> : nt == 2 ? (const void*)q3_program_kernel<2>
@@ -1669,6 +1688,8 @@ extern "C" int q3_describe_frame_program(q3_engine* e, int32_t* kinds, int32_t c
 
 // Debug/profiling: run a synthetic program made of `count` repetitions of the frame-program phases
 // [first, first+span) (mode 0, one pass) and return the elapsed device time.  Used by tools/icache_probe.py.
+extern "C" int q3_debug_set_skip(q3_engine* e, int32_t mask) { if (e) e->dbg_skip = mask; return 0; }
+
 extern "C" int q3_debug_time_phases(q3_engine* e, int32_t first, int32_t span, int32_t count, float* ms_out, void* stream_) {
   Q3_REQUIRE(e && e->prog_B > 0 && e->B > 0, "prefill first");
   Q3_REQUIRE(first >= 0 && span >= 1 && first + span <= (int)e->prog_frame.size() && count >= 1, "bad phase range");
