@@ -23,6 +23,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line (NCCL_DEBUG=VERSION prints a banner to stdout)
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -355,7 +356,8 @@ def main():
                                "sample": f"prefill B={B} + {args.cpu_frames} frame-steps + codec decode of {args.cpu_frames} frames, "
                                          f"fp32, {ncores} threads, extrapolated to {N} frames", **det}
     if rank == 0:
-        print(json.dumps(out))
+        sys.stdout.flush()
+        print(json.dumps(out), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -250,6 +250,12 @@ __device__ __forceinline__ void prefetch_phase_weights(const Phase& ph) {
   }
 }
 
+__device__ __forceinline__ uint32_t norm_pair(uint32_t x2, uint32_t w2, float inv) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(bf16lo(x2) * inv, bf16hi(x2) * inv);
+  __nv_bfloat162 r = __hmul2(t, *reinterpret_cast<const __nv_bfloat162*>(&w2));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
 // stage x (optionally RMS-normed) into smem as bf16 [col][K] (rows skewed by 64 B).  One warp per column; a lane
 // issues up to 8 independent 16-byte loads (K <= 2048 per pass) before touching the data; the RMSNorm runs on the
 // registers (sum of squares -> warp reduce -> scale) and the result is written to smem once.  The norm weights
@@ -283,16 +289,19 @@ __device__ __forceinline__ void stage_columns(const bf16* __restrict__ src, int 
           }
         }
         ss = warp_sum(ss);
+        PROF_MARK(7);
         const float inv = rsqrtf(ss / (float)K + eps);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (v0 + 32 * i < nv) {
+            // bf16(bf16(x*inv) * w): fp32 scale, one packed RN conversion, then a packed bf16 multiply (HMUL2.BF16
+            // rounds the exact product to nearest-even = the reference's bf16 x bf16 -> bf16 multiply)
             const uint4 w = nw_s[v0 + 32 * i];
             uint4 o;
-            o.x = pack_bf16(rbf(bf16lo(v[i].x) * inv) * bf16lo(w.x), rbf(bf16hi(v[i].x) * inv) * bf16hi(w.x));
-            o.y = pack_bf16(rbf(bf16lo(v[i].y) * inv) * bf16lo(w.y), rbf(bf16hi(v[i].y) * inv) * bf16hi(w.y));
-            o.z = pack_bf16(rbf(bf16lo(v[i].z) * inv) * bf16lo(w.z), rbf(bf16hi(v[i].z) * inv) * bf16hi(w.z));
-            o.w = pack_bf16(rbf(bf16lo(v[i].w) * inv) * bf16lo(w.w), rbf(bf16hi(v[i].w) * inv) * bf16hi(w.w));
+            o.x = norm_pair(v[i].x, w.x, inv);
+            o.y = norm_pair(v[i].y, w.y, inv);
+            o.z = norm_pair(v[i].z, w.z, inv);
+            o.w = norm_pair(v[i].w, w.w, inv);
             v[i] = o;
             if (save) reinterpret_cast<uint4*>(save + (size_t)col * K)[v0 + 32 * i] = o;
           }

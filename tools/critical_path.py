@@ -25,7 +25,8 @@ for i, k in enumerate(kinds):
     last = int(np.argmax(end))
     d = agg.setdefault(key, [])
     m = T[i, last, 2:6]
-    d.append(dict(phase=end.max() - rel_prev.min(), skew_release=rel_prev.max() - rel_prev.min(),
+    m7 = T[i, last, 7]
+    d.append(dict(ld=(m7 - T[i, last, 2]) if m7 > 0 else 0.0, nrm=(T[i, last, 3] - m7) if m7 > 0 else 0.0, phase=end.max() - rel_prev.min(), skew_release=rel_prev.max() - rel_prev.min(),
                   body_last=end[last] - rel_prev[last], body_med=np.median(end - rel_prev), body_min=(end - rel_prev).min(),
                   arrive_to_release=passed.min() - end.max(), release_spread=passed.max() - passed.min(),
                   seg=[(m[0] - rel_prev[last]) if m[0] > 0 else 0, (m[1] - m[0]) if m[1] > 0 else 0, (m[2] - m[1]) if m[2] > 0 else 0,
@@ -37,5 +38,6 @@ for k, v in agg.items():
     f = lambda n: np.mean([x[n] for x in v])
     seg = np.mean([x["seg"] for x in v], axis=0)
     tot += f("phase") * len(v)
+    print(f"   [stage split: loads->ss {f('ld'):.2f}  norm+sts+sync {f('nrm'):.2f}]", end="")
     print(f"{k:28s} {len(v):4d} {f('phase'):6.2f} {f('body_last'):9.2f} {f('body_med'):8.2f} {f('body_min'):8.2f} {f('arrive_to_release'):8.2f} {f('release_spread'):10.2f} | " + " ".join(f"{x:5.2f}" for x in seg))
 print(f"sum of phase times {tot:.0f} us")
