@@ -195,3 +195,23 @@ def test_full_shape_1p7b_two_frames():
             d = np.abs(cl[f, j] - r)
             assert d.max() < 0.2 * float(np.std(r)) and d.mean() < 0.05 * float(np.std(r)), (f, j, d.max(), d.mean())
     eng.close()
+
+
+def test_long_context_cross_cta_split_attention():
+    """ctx > 128 with few rows => the talker attention is split across CTAs (flash-decoding style) and combined by
+    the last arriver; checked against the oracle at ctx ~ 300 and ~ 600 (3 and 5 splits)."""
+    cfg = _tiny()
+    Wb, Wf = Hh.bf16_weights(OT.random_weights(cfg, seed=8))
+    for lens in ([300], [600, 150]):
+        B = len(lens)
+        embs, trail, pad = Hh.make_inputs(cfg, lens, [0] * B, seed=13)
+        N = 3
+        sp = OT.SamplingCfg(do_sample=False, subtalker_dosample=False, max_new_tokens=N + 1, suppress_eos=True)
+        ref = OT.generate(Wf, cfg, [e.float() for e in embs], [t.float() for t in trail], pad.float(), sp, record_logits=True)
+        forced = torch.stack(ref.codes).numpy()
+        eng = _engine(cfg, Wb, max_ctx=1024)
+        codes, tl, cl, prog = Hh.run_engine_forced(eng, embs, trail, pad, Hh.to_pkg_sampling(sp), forced, DEV)
+        assert prog[0] == N
+        for f in range(N + 1):
+            _check_logits(tl[f], ref.record["talker_logits"][f], f"ctx{lens} talker frame {f}")
+        eng.close()

@@ -84,3 +84,23 @@ def test_full_size_codec_default_config():
     snr = _snr_db(ref, out)
     assert torch.isfinite(out).all()
     assert snr > 22.0, f"SNR {snr:.1f} dB"
+
+
+def test_chunked_decode_beyond_300_frames_matches_oracle_chunking():
+    """> 300 frames: the reference decodes in 300-frame chunks with 25 frames of left context, which is NOT a full
+    causal forward; the engine replicates the chunking exactly (…v2.py:886-896)."""
+    from qwen3_tts_b200.codec import CodecDecoder
+    cfg = _small_cfg()
+    Wb, Wf = _bf16_round(OC.random_weights(cfg, seed=9))
+    g = torch.Generator().manual_seed(4)
+    codes = torch.randint(0, cfg.codebook_size, (1, 16, 330), generator=g)
+    ref = OC.chunked_decode(Wf, cfg, codes)
+    dec = CodecDecoder(_pkg_cfg(cfg), Wb, device=DEV, max_frames=512)
+    out = dec.chunked_decode(codes.to(DEV)).cpu()
+    assert out.shape == ref.shape == (1, 1, 330 * 1920)
+    assert _snr_db(ref, out) > 25.0
+    # and it differs from the un-chunked forward after the first chunk, exactly like the reference
+    full = dec.forward(codes.to(DEV)).cpu()
+    assert torch.equal(full[..., :300 * 1920], out[..., :300 * 1920])
+    assert not torch.equal(full[..., 300 * 1920:], out[..., 300 * 1920:])
+    dec.close()
