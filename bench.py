@@ -311,6 +311,16 @@ def main():
     h2d = sum(e.numel() * 2 for e in embs) + pad.numel() * 2
     d2h = sum(w.size * 4 for w in wavs_host)
 
+    # ---- first-packet latency (config[3]): prefill + 4 frame-steps + codec decode of the 4 frames, host in / host out
+    sp_fp = q.SamplingParams(max_new_tokens=5, suppress_eos=True, seed=1234, **spk)
+    for _ in range(2):
+        next(iter(eng.stream_synthesize(embs, trail, pad, sp_fp, packet_frames=4)))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        next(iter(eng.stream_synthesize(embs, trail, pad, sp_fp, packet_frames=4)))
+    first_packet_ms = (time.perf_counter() - t0) / 3 * 1000.0
+
     tms = torch.tensor([ms_total, e2e_s * 1000.0, t_dec], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -339,7 +349,7 @@ def main():
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
            "config": config_block(args, lens, world), "rtf": (ms_total / 1000.0) / (frames_total * FRAME_SEC),
            "breakdown_ms_per_step": {"prefill": t_pre / args.steps, "decode": t_dec / args.steps, "codec": t_cod / args.steps},
-           "roofline": roof,
+           "roofline": roof, "first_packet_ms": first_packet_ms,
            "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "rtf": (e2e_ms / 1000.0) / (frames_total * FRAME_SEC)},
            "gpu_launches": args.steps * (cfg.talker.num_layers * 8 + 2 + eng.codec.last_launches()),  # prefill (7 GEMM/row kernels + attention per layer) + head + fused decode + codec

@@ -53,6 +53,33 @@ class TTSEngine:
         out = [w.to(torch.float32).cpu().numpy() for w in wavs]
         return out, codes
 
+    @torch.no_grad()
+    def stream_synthesize(self, inputs_embeds, trailing_text, tts_pad_embed, sp: SamplingParams, packet_frames: int = 4,
+                          left_context: int = 25):
+        """Streaming OUTPUT (new surface: the reference returns audio whole).  Yields, per packet of
+        `packet_frames` frames (4 frames = 320 ms, Qwen3-TTS report §3.4), a list with one fp32 numpy waveform chunk per
+        row.  Each packet is decoded together with `left_context` already-emitted frames, exactly like the reference's
+        own chunked_decode does between chunks (…v2.py:886-896: 25 frames); `left_context=None` re-decodes the whole
+        prefix, which equals the one-shot causal decode bit for bit."""
+        dev = self.device
+        emb = [e.to(dev, non_blocking=True) for e in inputs_embeds]
+        tr = [t.to(dev, non_blocking=True) for t in trailing_text]
+        pad = tts_pad_embed.to(dev, non_blocking=True)
+        hist = [torch.zeros(0, self.codec_cfg.num_quantizers, dtype=torch.int64, device=dev) for _ in emb]
+        up = self.codec.total_upsample
+        for pkt in self.ar.stream(emb, tr, pad, sp, packet_frames=packet_frames):
+            out = []
+            for b, new in enumerate(pkt):
+                if new.shape[0] == 0:
+                    out.append(np.zeros(0, dtype=np.float32))
+                    continue
+                ctx = hist[b].shape[0] if left_context is None else min(left_context, hist[b].shape[0])
+                window = torch.cat([hist[b][hist[b].shape[0] - ctx:], new], 0)
+                wav = self.codec.forward(window.t()[None])[0, 0, ctx * up:]
+                out.append(wav.to(torch.float32).cpu().numpy())
+                hist[b] = torch.cat([hist[b], new], 0)
+            yield out
+
     def close(self):
         self.ar.close()
         self.codec.close()

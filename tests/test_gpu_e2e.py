@@ -59,3 +59,32 @@ def test_streaming_packets_equal_one_shot():
             parts[b].append(p)
     for b in range(len(emb)):
         assert torch.equal(torch.cat(parts[b]), one[b]) and one[b].shape == (13, 16)
+
+
+def test_stream_synthesize_full_prefix_equals_one_shot_decode():
+    """Packetised audio: with the whole prefix as left context the concatenated packets equal the one-shot causal
+    decode bit for bit (decoder causality); with the reference's 25-frame context the first packets
+    (<= 25 frames of history) are identical too."""
+    import qwen3_tts_b200 as q
+    from qwen3_tts_b200 import synthetic
+    from qwen3_tts_b200.pipeline import TTSEngine
+    cfg = synthetic.cfg_tiny()
+    ccfg = q.CodecConfig(codebook_size=2048, codebook_dim=64, hidden_size=64, latent_dim=64, num_heads=4, num_kv_heads=4,
+                         head_dim=16, sliding_window=6, intermediate_size=96, num_layers=2, decoder_dim=256)
+    eng = TTSEngine(cfg, synthetic.random_tts_weights(cfg, device=DEV, seed=0), ccfg,
+                    synthetic.random_codec_weights(ccfg, device=DEV, seed=0), device=DEV, max_batch=4, max_ctx=128, codec_max_frames=64)
+    H = cfg.talker.hidden_size
+    g = torch.Generator().manual_seed(1)
+    embs = [(torch.randn(n, H, generator=g) * 0.5).bfloat16() for n in (5, 8)]
+    trail = [torch.zeros(0, H, dtype=torch.bfloat16)] * 2
+    pad = (torch.randn(H, generator=g) * 0.1).bfloat16()
+    sp = q.SamplingParams(max_new_tokens=11, suppress_eos=True, seed=5)
+    wavs, codes = eng.synthesize(embs, trail, pad, sp)
+    for lc in (None, 25):
+        parts = [[] for _ in embs]
+        for pkt in eng.stream_synthesize(embs, trail, pad, sp, packet_frames=4, left_context=lc):
+            for b, w in enumerate(pkt):
+                parts[b].append(w)
+        for b in range(2):
+            assert np.array_equal(np.concatenate(parts[b]), wavs[b])
+    eng.close()
