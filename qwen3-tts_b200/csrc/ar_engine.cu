@@ -41,7 +41,7 @@ int q3_set_err(const char* fmt, ...) {
 
 namespace {
 
-constexpr int NTHREADS = 512;
+constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
 constexpr int HD = 128;          // head_dim (required)
 constexpr int MAXB = Q3_MAX_BATCH;
@@ -314,7 +314,7 @@ __device__ __forceinline__ void stage_columns(const bf16* __restrict__ src, int 
   }
 }
 
-constexpr int DEPTH = 4;  // k32-blocks (2 x 16 B per lane each) kept in flight per warp
+constexpr int DEPTH = (NTHREADS <= 256) ? 8 : 4;  // k32-blocks (2 x 16 B per lane each) kept in flight per warp
 
 __device__ __forceinline__ void gemv_preload(uint4 (&a)[DEPTH][2], const uint4* __restrict__ wp, int nk) {
 #pragma unroll
@@ -592,7 +592,7 @@ __device__ __noinline__ void attn_phase(const Phase& ph, const KParams& P, unsig
       // warp-uniform trip count (full-mask shuffles below); each half-warp handles 2 tokens per iteration so
       // that 4 independent 16-byte loads are in flight before the dependent softmax update
 #pragma unroll 1
-      for (int tb = s0 + warp * 4; tb < e1; tb += 64) {
+      for (int tb = s0 + warp * 4; tb < e1; tb += NWARPS * 4) {
         const int tk0 = tb + (lane >> 4), tk1 = tk0 + 2;
         uint4 kv[2], vv[2];
         kv[0] = kv[1] = vv[0] = vv[1] = make_uint4(0, 0, 0, 0);
@@ -646,7 +646,7 @@ __device__ __noinline__ void attn_phase(const Phase& ph, const KParams& P, unsig
       float M = -INFINITY, L = 0.f, O = 0.f;
       // token t of this split maps to half-warp ((t>>2)<<1) | (t&1): only the first nhw half-warps hold data
       const int ntok = max(e1 - s0, 0);
-      const int nhw = min(32, ((ntok + 3) >> 2) << 1);
+      const int nhw = min(2 * NWARPS, ((ntok + 3) >> 2) << 1);
       if (rr_ < R) {
 #pragma unroll 2
         for (int h2 = 0; h2 < nhw; ++h2) M = fmaxf(M, red[((size_t)h2 * RMAX + rr_) * 130]);
