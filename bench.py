@@ -16,6 +16,7 @@ the restated loop — the HF generate loop cannot run under transformers 5.5.0, 
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -339,8 +340,20 @@ def main():
     else:
         peak = 6650.0; peak_src = "fallback 6.65 TB/s (B200_PROFILING.md)"
     achieved = a_bytes / t_step / 1e9
+    # measured DRAM traffic of this kernel from the committed `ncu --set full` capture (profiles/): bytes per
+    # frame-step of the B=8 capture (16 frame-steps per launch) scaled to this launch's frame count; null otherwise
+    traffic = None
+    try:
+        if args.batch == 8 and args.model == "1.7b":
+            txt = open(os.path.join(ROOT, "profiles", "r01_decode_kernel_ncu_full.txt")).read()
+            rd = float(re.search(r"^dram__bytes_read\.sum,([0-9.]+),Gbyte", txt, re.M).group(1)) * 1e9
+            wr = float(re.search(r"^dram__bytes_write\.sum,([0-9.]+),Mbyte", txt, re.M).group(1)) * 1e6
+            traffic = (rd + wr) / 16.0 * N
+    except Exception:
+        traffic = None
     roof = {"bound": "hbm", "kernel": "q3_program_kernel (fused frame-step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+            "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+            "traffic_source": "profiles/r01_decode_kernel_ncu_full.txt (ncu --set full, per frame-step x frames)" if traffic else None,
             "algorithmic_bytes_per_launch": a_bytes * N, "algorithmic_bytes_per_frame_step": a_bytes,
             "no_residency_bytes_per_frame_step": a_stream, "ms_per_frame_step": t_step * 1e3, "mean_context": S_mean}
 
