@@ -131,6 +131,9 @@ struct KParams {
   const bf16* emb_t;        // talker codec_embedding [V][H]
   const bf16* emb_cp;       // cp codec_embedding [G-1][Vc][H]
   bf16* x_cp;               // CP input [2][B][H]
+  const bf16* cp_next;      // rows fed to passes >= 1: projected embedding table [(G-1)*Vc][Hc] or emb_cp itself
+  bf16* cp_next_dst;        // where they go: cp.h (table / Identity projection) or x_cp (projection phase follows)
+  int cp_next_w;            // row width of cp_next / cp_next_dst
   bf16* past_hidden;        // [B][H]
   const bf16* trailing;     // [B][stride][H]
   int trailing_stride;
@@ -940,10 +943,12 @@ __device__ __noinline__ void sample_phase(const Phase& ph, const KParams& P, uns
     const int Vc = P.cp.vocab;
     if (j < P.G - 1) {
       // input of the next pass: codec_embedding[j-1](c_j)  (:1281)
-      const bf16* e = P.emb_cp + ((size_t)(j - 1) * Vc + tok) * H;
-      bf16* x = P.x_cp + (size_t)b * H;
+      // (with the projection table the row is small_to_mtp_projection(embedding) already, :1283, and lands in cp.h)
+      const int Wn = P.cp_next_w;
+      const bf16* e = P.cp_next + ((size_t)(j - 1) * Vc + tok) * Wn;
+      bf16* x = P.cp_next_dst + (size_t)b * Wn;
 #pragma unroll 1
-      for (int i = tid * 8; i < H; i += NTHREADS * 8)
+      for (int i = tid * 8; i < Wn; i += NTHREADS * 8)
         *reinterpret_cast<uint4*>(x + i) = *reinterpret_cast<const uint4*>(e + i);
     } else {
       // next talker input: sum of the 16 codebook embeddings (fp32 sum, one bf16 rounding) + text (:1682-1692)
@@ -1151,6 +1156,11 @@ __global__ void pf_attention_kernel(const bf16* __restrict__ qkv, bf16* __restri
 // ------------------------------------------------------------------------------------------------
 // weight packing: row-major [N][K] bf16 -> stream of (16 rows x 32 k) 1 KB blocks, each two 8x32 halves
 // ------------------------------------------------------------------------------------------------
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = bf2f(src[i]);
+}
+
 __global__ void pack_weight_kernel(const bf16* __restrict__ src, uint4* __restrict__ dst, int N, int K) {
   // one thread per 16-byte chunk of the destination
   const size_t total = (size_t)N * K / 8;
@@ -1204,6 +1214,8 @@ struct q3_engine {
   // programs (host copies) for the current batch size
   int prog_B = -1;
   int dbg_skip = 0;
+  bool use_proj_tab = true;   // Q3_CP_PROJ_TAB=0 keeps the projection GEMV in passes >= 1 (A/B knob)
+  bf16* proj_tab = nullptr;   // small_to_mtp_projection(cp.codec_embedding) [(G-1)*Vc][Hc], built once at finalize
   std::vector<Phase> prog_layers, prog_head, prog_frame;
   int off_layers = 0, off_head = 0, off_frame = 0;
   q3_sampling sp{};
@@ -1273,6 +1285,7 @@ extern "C" int q3_engine_create(const q3_engine_cfg* cfg, q3_engine** out) {
     const int v = atoi(g);
     if (v >= 8 && v <= e->sm_count) e->sm_count = v;
   }
+  if (const char* f = getenv("Q3_CP_PROJ_TAB")) e->use_proj_tab = atoi(f) != 0;
   Q3_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
   if (gemm_init()) return 1;
   if (e->alloc(&e->st, 1)) return 1;
@@ -1321,7 +1334,7 @@ extern "C" int q3_engine_load_tensor(q3_engine* e, const char* name, const void*
     Q3_CUDA(cudaGetLastError());
     Q3_CUDA(cudaStreamSynchronize(e->copy_stream));
     e->packed[n] = pw;
-    if (n.rfind("talker.layers.", 0) == 0) {  // prefill GEMM operand: the source layout [N][K] is already K-major
+    if (n.rfind("talker.layers.", 0) == 0 || (n == "cp.proj" && cols % 64 == 0)) {  // tcgen05 GEMM operand: [N][K] is already K-major
       Q3_REQUIRE(cols % 64 == 0, "%s: K must be a multiple of 64 for the prefill GEMM", name);
       bf16* g = nullptr;
       if (e->alloc(&g, (size_t)rows * cols)) return 1;
@@ -1427,9 +1440,11 @@ static int build_programs(q3_engine* e, int B) {
   // bias-GEMV writes the projected rows into cp.h; with the Identity projection (0.6B, H == Hc) x IS cp.h
   // (e->x_cp_ptr() aliases it) and the layers run in place on the block they need.
   bf16* xin = c.has_cp_projection ? e->x_cp : C.h;
-  auto cp_pass = [&](int ncmode, int nq, int ctx_end, int block) -> bf16* {
+  auto cp_pass = [&](int ncmode, int nq, int ctx_end, int block, bool from_table = false) -> bf16* {
     bf16* hb = C.h;
-    if (c.has_cp_projection) {
+    if (from_table) {
+      // the previous sample phase already wrote the projected embedding rows into cp.h
+    } else if (c.has_cp_projection) {
       F.push_back(gemv(wproj, xin + (size_t)block * B * H, H, nullptr, 0.f, C.h, Hc, EPI_BIAS, ncmode, bproj));
     } else {
       hb = C.h + (size_t)block * B * Hc;
@@ -1450,7 +1465,7 @@ static int build_programs(q3_engine* e, int B) {
         if (!(hb = cp_pass(NC_B, 1, 2, 1))) return 1;
       }
     } else {
-      if (!(hb = cp_pass(NC_B, 1, j + 2, 0))) return 1;
+      if (!(hb = cp_pass(NC_B, 1, j + 2, 0, e->proj_tab != nullptr))) return 1;
     }
     F.push_back(gemv(wlm, hb, Hc, cnorm, C.eps, C.logits, C.vocab, EPI_LOGITS, NC_B));
     Phase s{}; s.type = PH_SAMPLE; s.group = j + 1;
@@ -1498,6 +1513,26 @@ extern "C" int q3_engine_finalize(q3_engine* e) {
   if (need_plain(e, "cp.codec_embedding",
                  (int64_t)(c.num_code_groups - 1) * c.cp.vocab_size * c.talker.hidden_size, &p))
     return 1;
+  // projection table: passes >= 1 of the code predictor feed small_to_mtp_projection(codec_embedding[j-1](c_j)) (:1281-1283),
+  // a function of the sampled id only -> one tcgen05 GEMM over all (G-1)*Vc embedding rows here, no GEMV phase per pass
+  if (c.has_cp_projection && e->use_proj_tab && e->gemm_w.count("cp.proj") && !e->proj_tab) {
+    const int H = c.talker.hidden_size, Hc = c.cp.hidden_size;
+    const int rows = (c.num_code_groups - 1) * c.cp.vocab_size;
+    const bf16* bproj;
+    if (need_plain(e, "cp.proj_bias", Hc, &bproj)) return 1;
+    float* bias_f = nullptr;
+    if (e->alloc(&bias_f, (size_t)Hc) || e->alloc(&e->proj_tab, (size_t)rows * Hc)) return 1;
+    bf16_to_f32_kernel<<<(Hc + 255) / 256, 256, 0, e->copy_stream>>>(bproj, bias_f, Hc);
+    GemmEpilogue ep{};
+    ep.bias = bias_f; ep.cmod = Hc; ep.out_raw = e->proj_tab;
+    GemmPlan plan;
+    const int zero = 0;
+    if (gemm_make_plan(&plan, p, 1, rows, H, H, (int64_t)rows * H, e->gemm_w["cp.proj"], Hc, H, 1, &zero,
+                       gemm_pick_bn(Hc, (rows + 127) / 128, 1), ep))
+      return 1;
+    if (gemm_launch(plan, e->copy_stream)) return 1;
+    Q3_CUDA(cudaStreamSynchronize(e->copy_stream));
+  }
   if (build_programs(e, 1)) return 1;
   // kernel attributes
   Q3_CUDA(cudaFuncSetAttribute(q3_program_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_nt(1)));
@@ -1529,6 +1564,8 @@ static int launch_program(q3_engine* e, int off, int n, int mode, int max_iters,
   for (int b = 0; b < MAXB; ++b) { P.len0[b] = e->len0[b]; P.trailing_len[b] = e->trailing_len[b]; }
   P.emb_t = e->plain["talker.codec_embedding"]; P.emb_cp = e->plain["cp.codec_embedding"];
   P.x_cp = e->cfg.has_cp_projection ? e->x_cp : e->cp.h; P.past_hidden = e->past_hidden; P.trailing = e->trailing; P.trailing_stride = e->trailing_cap;
+  if (e->proj_tab) { P.cp_next = e->proj_tab; P.cp_next_dst = e->cp.h; P.cp_next_w = e->cfg.cp.hidden_size; }
+  else { P.cp_next = P.emb_cp; P.cp_next_dst = P.x_cp; P.cp_next_w = e->cfg.talker.hidden_size; }
   P.tts_pad = e->tts_pad; P.seen = e->seen; P.codes_out = codes_dev; P.codes_stride = e->codes_stride;
   P.split_buf = e->split_buf; P.forced = e->forced; P.n_forced = e->n_forced; P.dbg_tlogits = e->dbg_t; P.dbg_clogits = e->dbg_c; P.prof = (mode == 1) ? e->prof : nullptr; P.dbg_skip = e->dbg_skip;
   Q3_CUDA(cudaMemsetAsync(&e->st->bar_count, 0, sizeof(unsigned int), stream));
