@@ -156,6 +156,45 @@ int q3_codec_total_upsample(q3_codec* c);
 /* kernels launched by the last q3_codec_forward (bench.py's gpu_launches bookkeeping) */
 int q3_codec_last_launch_count(q3_codec* c);
 
+/* ---------------------------------------------------------------- codec ENCODER (Qwen3TTSTokenizer.encode)
+ * Replaces Qwen3TTSTokenizerV2Model.encode (core/tokenizer_12hz/modeling_qwen3_tts_tokenizer_v2.py:961-991), i.e.
+ * transformers MimiModel._encode_frame (modeling_mimi.py:1455-1488), restricted to the first
+ * `encoder_valid_num_quantizers` levels (the reference computes 32 and keeps 16, :981-983).  fp32 end to end:
+ * the output is discrete (nearest-centroid indices), see csrc/codec_encoder.cu. */
+typedef struct {
+  int32_t num_filters, kernel_size, last_kernel_size, residual_kernel_size, compress; /* MimiConfig SEANet fields */
+  int32_t n_ratios, ratios[8];        /* downsampling strides in encoder order = reversed(upsampling_ratios): 4,5,6,8 */
+  int32_t hidden_size, num_layers, num_heads, head_dim, intermediate_size, sliding_window;
+  float norm_eps;
+  int32_t codebook_size, codebook_dim;
+  int32_t num_semantic_quantizers;    /* 1 */
+  int32_t num_quantizers;             /* levels to compute = encoder_valid_num_quantizers (16) */
+  int32_t downsample_stride;          /* encodec_frame_rate / frame_rate = 2 */
+  int32_t max_frames;                 /* rows of the RoPE tables (transformer frames, 25 Hz) */
+  int32_t device;
+} q3_codec_enc_cfg;
+typedef struct q3_codec_enc q3_codec_enc;
+
+int q3_codec_enc_create(const q3_codec_enc_cfg* cfg, q3_codec_enc** out);
+void q3_codec_enc_destroy(q3_codec_enc* e);
+/* fp32 device tensors, engine-native names (qwen3-tts_b200/codec_encoder.py::_load maps MimiModel's state_dict):
+ *   "enc.conv0|enc.res<i>.a|enc.res<i>.b|enc.down<i>|enc.conv_last" + ".w" [Cout][Cin][k] / ".b" [Cout];
+ *   "tr.<l>.ln1.w/.b", "tr.<l>.qkv.w" [3C][C] = cat(q,k,v), "tr.<l>.o.w", "tr.<l>.ls1", "tr.<l>.ln2.w/.b",
+ *   "tr.<l>.fc1.w" [I][C], "tr.<l>.fc2.w" [C][I], "tr.<l>.ls2"; "rope.cos|sin" [max_frames][head_dim/2];
+ *   "down.w" [C][C][2*stride]; "rvq.sem.proj.w|rvq.ac.proj.w" [D][C]; per level q (0 = semantic):
+ *   "rvq.<q>.e" [K][D] = embed_sum / clamp(cluster_usage, 1e-5), "rvq.<q>.et" [D][K], "rvq.<q>.e2" [K] = |e|^2. */
+int q3_codec_enc_load_tensor(q3_codec_enc* e, const char* name, const float* dev, const int64_t* shape, int32_t ndim);
+int q3_codec_enc_finalize(q3_codec_enc* e);
+/* wav: fp32 [B][T] device (rows right-padded with zeros: every layer is causal, so padding never reaches earlier
+ * frames); codes: int32 [B][num_quantizers][q3_codec_enc_frames(T)] device.  Asynchronous. */
+int q3_codec_enc_encode(q3_codec_enc* e, const float* wav_dev, int32_t B, int32_t T, int32_t* codes_dev, void* stream);
+int q3_codec_enc_frames(q3_codec_enc* e, int32_t T);   /* ceil-chain through every stride */
+int q3_codec_enc_hop(q3_codec_enc* e);                 /* samples per frame (1920) */
+int q3_codec_enc_last_launch_count(q3_codec_enc* e);
+/* Test hook: copy the activation [B][C][T] after stage `stage` (conv0, per ratio [res, down], conv_last, one per
+ * transformer layer, downsample) of the next encode into dst; stage < 0 clears all captures. */
+int q3_codec_enc_debug_capture(q3_codec_enc* e, int32_t stage, float* dst_dev, int64_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,7 @@ import numpy as np
 import torch
 
 from . import codec as OC
+from . import mimi_encoder as OM
 from . import ref_driver as R
 from . import talker as OT
 
@@ -100,7 +101,37 @@ def make_codec():
     print("codec_micro.npz", wav.shape, float(wav.abs().max()))
 
 
+def micro_encoder_cfg():
+    return OM.MimiEncCfg(num_filters=4, hidden_size=32, num_layers=2, num_heads=2, head_dim=16, intermediate_size=48,
+                         sliding_window=5, codebook_size=32, codebook_dim=16, num_quantizers=32, valid_num_quantizers=16)
+
+
+def make_encoder():
+    """Golden codes from the third-party encoder the reference wraps: transformers MimiModel (installed 5.5.0; the
+    reference pins 4.57.3) driven exactly like Qwen3TTSTokenizerV2Model.encode (…v2.py:977-983)."""
+    from transformers import MimiConfig, MimiModel
+    cfg = micro_encoder_cfg()
+    W = OM.random_weights(cfg, seed=17)
+    hf = MimiModel(MimiConfig(**cfg.to_hf_kwargs())).eval()
+    missing, unexpected = hf.load_state_dict(W, strict=False)
+    assert not unexpected, unexpected
+    g = torch.Generator().manual_seed(4)
+    wav = (torch.randn(2, 15000, generator=g) * 0.1).clamp(-1, 1)  # 16 transformer frames > window 5, 8 code frames
+    with torch.no_grad():
+        codes = hf.encode(wav[:, None, :], return_dict=True).audio_codes[:, : cfg.valid_num_quantizers]
+    blob = {f"W::{k}": v.numpy() for k, v in W.items()}
+    blob.update(wav=wav.numpy(), codes=codes.numpy())
+    np.savez_compressed(os.path.join(OUT, "encoder_micro.npz"), **blob)
+    print("encoder_micro.npz", tuple(codes.shape))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    make_talker()
-    make_codec()
+    import sys
+    which = sys.argv[1:] or ["talker", "codec", "encoder"]
+    if "talker" in which:
+        make_talker()
+    if "codec" in which:
+        make_codec()
+    if "encoder" in which:
+        make_encoder()

@@ -39,12 +39,26 @@ class CodecCfg(C.Structure):
                 ("max_frames", C.c_int32), ("max_batch", C.c_int32), ("device", C.c_int32)]
 
 
+class CodecEncCfg(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("num_filters", "kernel_size", "last_kernel_size", "residual_kernel_size",
+                                          "compress", "n_ratios")] + \
+               [("ratios", C.c_int32 * 8)] + \
+               [(n, C.c_int32) for n in ("hidden_size", "num_layers", "num_heads", "head_dim", "intermediate_size",
+                                          "sliding_window")] + \
+               [("norm_eps", C.c_float)] + \
+               [(n, C.c_int32) for n in ("codebook_size", "codebook_dim", "num_semantic_quantizers", "num_quantizers",
+                                          "downsample_stride", "max_frames", "device")]
+
+
 # every symbol include/qwen3tts_b200.h declares (tests/test_abi.py checks the header against this list)
 AR_SYMBOLS = ["q3_abi_version", "q3_last_error", "q3_engine_create", "q3_engine_destroy", "q3_engine_load_tensor",
               "q3_engine_finalize", "q3_prefill", "q3_decode", "q3_get_progress", "q3_set_debug",
               "q3_algorithmic_bytes", "q3_set_profile", "q3_describe_frame_program", "q3_debug_time_phases", "q3_debug_set_skip"]
 CODEC_SYMBOLS = ["q3_codec_create", "q3_codec_destroy", "q3_codec_load_tensor", "q3_codec_finalize",
-                 "q3_codec_forward", "q3_codec_total_upsample", "q3_codec_last_launch_count"]
+                 "q3_codec_forward", "q3_codec_total_upsample", "q3_codec_last_launch_count",
+                 "q3_codec_enc_create", "q3_codec_enc_destroy", "q3_codec_enc_load_tensor", "q3_codec_enc_finalize",
+                 "q3_codec_enc_encode", "q3_codec_enc_frames", "q3_codec_enc_hop", "q3_codec_enc_last_launch_count",
+                 "q3_codec_enc_debug_capture"]
 
 _lib = None
 
@@ -92,6 +106,16 @@ def load():
         lib.q3_codec_forward.argtypes = [vp, vp, i32, i32, vp, vp]
         lib.q3_codec_total_upsample.argtypes = [vp]
         lib.q3_codec_last_launch_count.argtypes = [vp]
+        lib.q3_codec_enc_create.argtypes = [C.POINTER(CodecEncCfg), C.POINTER(vp)]
+        lib.q3_codec_enc_destroy.argtypes = [vp]
+        lib.q3_codec_enc_destroy.restype = None
+        lib.q3_codec_enc_load_tensor.argtypes = [vp, C.c_char_p, vp, C.POINTER(i64), i32]
+        lib.q3_codec_enc_finalize.argtypes = [vp]
+        lib.q3_codec_enc_encode.argtypes = [vp, vp, i32, i32, vp, vp]
+        lib.q3_codec_enc_frames.argtypes = [vp, i32]
+        lib.q3_codec_enc_hop.argtypes = [vp]
+        lib.q3_codec_enc_last_launch_count.argtypes = [vp]
+        lib.q3_codec_enc_debug_capture.argtypes = [vp, i32, vp, i64]
     _lib = lib
     return lib
 

@@ -117,3 +117,46 @@ class CodecConfig:
                            dc.num_attention_heads, dc.num_key_value_heads, hd, dc.sliding_window,
                            dc.intermediate_size, float(dc.rms_norm_eps), dc.num_hidden_layers, dc.num_quantizers,
                            tuple(dc.upsample_rates), tuple(dc.upsampling_ratios), dc.decoder_dim)
+
+
+@dataclass
+class EncoderConfig:
+    """The codec ENCODER = transformers MimiConfig (the reference builds MimiConfig(**encoder_config),
+    core/tokenizer_12hz/configuration_qwen3_tts_tokenizer_v2.py:155-162) + encoder_valid_num_quantizers (:147)."""
+    num_filters: int = 64
+    kernel_size: int = 7
+    last_kernel_size: int = 3
+    residual_kernel_size: int = 3
+    compress: int = 2
+    ratios: Tuple[int, ...] = (4, 5, 6, 8)      # encoder order = reversed(MimiConfig.upsampling_ratios)
+    hidden_size: int = 512
+    num_layers: int = 8
+    num_heads: int = 8
+    head_dim: int = 64
+    intermediate_size: int = 2048
+    sliding_window: int = 250
+    rope_theta: float = 10000.0
+    norm_eps: float = 1e-5
+    codebook_size: int = 2048
+    codebook_dim: int = 256
+    num_semantic_quantizers: int = 1
+    valid_num_quantizers: int = 16
+    downsample_stride: int = 2
+    max_position_embeddings: int = 8000
+    encode_downsample_rate: int = 1920
+
+    @staticmethod
+    def from_hf(mc, valid_num_quantizers=16, encode_downsample_rate=1920):
+        """mc: a transformers MimiConfig (Qwen3TTSTokenizerV2Config.encoder_config)."""
+        rp = getattr(mc, "rope_parameters", None) or {}
+        theta = rp.get("rope_theta") if isinstance(rp, dict) else None
+        theta = theta or getattr(mc, "rope_theta", None) or 10000.0
+        if getattr(mc, "num_residual_layers", 1) != 1 or getattr(mc, "use_conv_shortcut", False) or \
+                not getattr(mc, "use_causal_conv", True) or mc.num_key_value_heads != mc.num_attention_heads:
+            raise ValueError("unsupported MimiConfig variant (need 1 residual layer, identity shortcut, causal convs, MHA)")
+        return EncoderConfig(mc.num_filters, mc.kernel_size, mc.last_kernel_size, mc.residual_kernel_size, mc.compress,
+                             tuple(reversed(list(mc.upsampling_ratios))), mc.hidden_size, mc.num_hidden_layers,
+                             mc.num_attention_heads, mc.head_dim, mc.intermediate_size, mc.sliding_window, float(theta),
+                             float(mc.norm_eps), mc.codebook_size, mc.codebook_dim, mc.num_semantic_quantizers,
+                             int(valid_num_quantizers), int(round(mc.encodec_frame_rate / mc.frame_rate)),
+                             mc.max_position_embeddings, int(encode_downsample_rate))

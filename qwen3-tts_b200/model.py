@@ -208,10 +208,17 @@ class Qwen3TTSForConditionalGenerationB200:
 class Qwen3TTSTokenizer:
     """inference/qwen3_tts_tokenizer.py:44 — decode path on the B200 codec engine."""
 
-    def __init__(self, cfg: CodecConfig, weights, device="cuda:0", max_frames=1024):
+    def __init__(self, cfg: CodecConfig, weights, device="cuda:0", max_frames=1024, encoder_cfg=None,
+                 encoder_weights=None):
+        """`encoder_cfg` / `encoder_weights` (EncoderConfig + MimiModel-named state dict) enable encode(); without
+        them the wrapper is decode-only (what TTS generation needs)."""
         self.config = cfg
         self.device = torch.device(device)
         self.decoder = CodecDecoder(cfg, weights, device=device, max_frames=max_frames)
+        self.encoder = None
+        if encoder_cfg is not None:
+            from .codec_encoder import CodecEncoder
+            self.encoder = CodecEncoder(encoder_cfg, encoder_weights, device=device)
 
     def get_model_type(self):
         return "qwen3_tts_tokenizer_12hz"
@@ -228,9 +235,89 @@ class Qwen3TTSTokenizer:
     def get_decode_upsample_rate(self):
         return self.config.total_upsample
 
+    # ---- audio input normalisation (inference/qwen3_tts_tokenizer.py:100-207), host-only
+    @staticmethod
+    def _is_probably_base64(s: str) -> bool:
+        return s.startswith("data:audio") or (("/" not in s and "\\" not in s) and len(s) > 256)
+
+    @staticmethod
+    def _is_url(s: str) -> bool:
+        from urllib.parse import urlparse
+        try:
+            u = urlparse(s)
+            return u.scheme in ("http", "https") and bool(u.netloc)
+        except Exception:
+            return False
+
+    @staticmethod
+    def _resample(a: np.ndarray, sr: int, target_sr: int) -> np.ndarray:
+        """The reference calls librosa.resample (soxr); neither is in this image, so a polyphase FIR resampler
+        (scipy.signal.resample_poly) stands in — same rate change, not bit-identical samples."""
+        if int(sr) == int(target_sr):
+            return a.astype(np.float32)
+        from math import gcd
+        from scipy.signal import resample_poly
+        g = gcd(int(sr), int(target_sr))
+        return resample_poly(a.astype(np.float32), int(target_sr) // g, int(sr) // g).astype(np.float32)
+
+    @classmethod
+    def load_audio(cls, x: str, target_sr: int) -> np.ndarray:
+        """:121-157 — wav path, URL or base64 (raw / data URL) -> mono float32 at target_sr.  PCM/float WAV only here
+        (scipy.io.wavfile; the reference's soundfile/librosa also read flac/ogg/mp3)."""
+        import base64
+        import io
+        from scipy.io import wavfile
+        if cls._is_url(x):
+            import urllib.request
+            with urllib.request.urlopen(x) as resp:
+                src = io.BytesIO(resp.read())
+        elif cls._is_probably_base64(x):
+            if "," in x and x.strip().startswith("data:"):
+                x = x.split(",", 1)[1]
+            src = io.BytesIO(base64.b64decode(x))
+        else:
+            src = x
+        sr, audio = wavfile.read(src)
+        if audio.dtype.kind == "i":
+            audio = audio.astype(np.float32) / float(np.iinfo(audio.dtype).max + 1)
+        elif audio.dtype.kind == "u":  # 8-bit PCM is unsigned
+            audio = (audio.astype(np.float32) - 128.0) / 128.0
+        audio = audio.astype(np.float32)
+        if audio.ndim > 1:
+            audio = np.mean(audio, axis=-1)
+        return cls._resample(audio, sr, target_sr)
+
+    @classmethod
+    def _normalize_audio_inputs(cls, audios, sr, target_sr=24000) -> List[np.ndarray]:
+        """:159-207 — str | ndarray | list of either -> list of 1-D float32 waveforms at target_sr."""
+        if isinstance(audios, (str, np.ndarray)):
+            audios = [audios]
+        if len(audios) == 0:
+            return []
+        if isinstance(audios[0], str):
+            return [cls.load_audio(x, target_sr) for x in audios]
+        if sr is None:
+            raise ValueError("For numpy waveform input, you must provide `sr` (original sampling rate).")
+        out = []
+        for a in audios:
+            if not isinstance(a, np.ndarray):
+                raise TypeError("Mixed input types are not supported. Use all paths/base64 or all numpy arrays.")
+            if a.ndim > 1:
+                a = np.mean(a, axis=-1)
+            out.append(cls._resample(a.astype(np.float32), int(sr), target_sr))
+        return out
+
     def encode(self, audios, sr=None, return_dict=True):
-        raise NotImplementedError("codec ENCODER (transformers MimiModel, third-party) is a 'next' row (SURVEY §8f-1); "
-                                  "use the reference encoder and pass its audio_codes to decode()")
+        """:208-257 -> Qwen3TTSTokenizerV2Model.encode (…v2.py:961-991): returns an object with
+        `.audio_codes = List[LongTensor (T_i, 16)]` on the device (or the 1-tuple when return_dict=False)."""
+        if self.encoder is None:
+            raise RuntimeError("this tokenizer was built without encoder weights (decode-only)")
+        wavs = self._normalize_audio_inputs(audios, sr, self.get_input_sample_rate())
+        codes = self.encoder.encode([torch.from_numpy(w) for w in wavs])
+        if not return_dict:
+            return (codes,)
+        from types import SimpleNamespace
+        return SimpleNamespace(audio_codes=codes)
 
     def decode(self, encoded) -> Tuple[List[np.ndarray], int]:
         """:259-365 — accepts an encode()-style output (has .audio_codes), a dict or a list of dicts whose

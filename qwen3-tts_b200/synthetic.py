@@ -152,3 +152,61 @@ def random_codec_weights(cfg: CodecConfig, device="cuda:0", seed=0, dtype=torch.
     conv(f"decoder.{n + 2}.conv", 1, cl, 7)
     W[f"decoder.{n + 2}.conv.weight"] *= 0.3
     return W
+
+
+def cfg_encoder_tiny():
+    from .config import EncoderConfig
+    return EncoderConfig(num_filters=8, hidden_size=64, num_layers=2, num_heads=4, head_dim=16, intermediate_size=96,
+                         sliding_window=6, codebook_size=64, codebook_dim=32)
+
+
+def random_encoder_weights(cfg, seed=0):
+    """Seeded fp32 weights under MimiModel's state_dict names (encoder half), CPU tensors (same recipe as
+    oracle/mimi_encoder.py:random_weights, restated — the product never imports oracle/)."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    W = {}
+
+    def rn(*shape, s=1.0):
+        return torch.randn(*shape, generator=g) * s
+
+    def conv(name, cin, cout, k):
+        W[f"{name}.conv.weight"] = rn(cout, cin, k, s=1.0 / math.sqrt(cin * k))
+        W[f"{name}.conv.bias"] = rn(cout, s=0.05)
+
+    idx = 0
+    conv(f"encoder.layers.{idx}", 1, cfg.num_filters, cfg.kernel_size)
+    idx += 1
+    dim = cfg.num_filters
+    for r in cfg.ratios:
+        conv(f"encoder.layers.{idx}.block.1", dim, dim // cfg.compress, cfg.residual_kernel_size)
+        conv(f"encoder.layers.{idx}.block.3", dim // cfg.compress, dim, 1)
+        idx += 2
+        conv(f"encoder.layers.{idx}", dim, dim * 2, 2 * r)
+        idx += 1
+        dim *= 2
+    idx += 1
+    conv(f"encoder.layers.{idx}", dim, cfg.hidden_size, cfg.last_kernel_size)
+    C, I = cfg.hidden_size, cfg.intermediate_size
+    for l in range(cfg.num_layers):
+        p = f"encoder_transformer.layers.{l}."
+        for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            W[p + f"self_attn.{n}.weight"] = rn(C, C, s=1.0 / math.sqrt(C))
+        W[p + "mlp.fc1.weight"] = rn(I, C, s=1.0 / math.sqrt(C))
+        W[p + "mlp.fc2.weight"] = rn(C, I, s=1.0 / math.sqrt(I))
+        for n in ("input_layernorm", "post_attention_layernorm"):
+            W[p + n + ".weight"] = 1.0 + rn(C, s=0.1)
+            W[p + n + ".bias"] = rn(C, s=0.05)
+        W[p + "self_attn_layer_scale.scale"] = 0.3 + rn(C, s=0.05)
+        W[p + "mlp_layer_scale.scale"] = 0.3 + rn(C, s=0.05)
+    W["downsample.conv.weight"] = rn(C, C, 2 * cfg.downsample_stride, s=1.0 / math.sqrt(C * 4))
+    D, K = cfg.codebook_dim, cfg.codebook_size
+    nsem = cfg.num_semantic_quantizers
+    for which, n in (("semantic", nsem), ("acoustic", cfg.valid_num_quantizers - nsem)):
+        p = f"quantizer.{which}_residual_vector_quantizer."
+        W[p + "input_proj.weight"] = rn(D, C, 1, s=1.0 / math.sqrt(C))
+        for qi in range(n):
+            usage = torch.rand(K, generator=g) * 3 + 0.5
+            W[p + f"layers.{qi}.codebook.cluster_usage"] = usage
+            W[p + f"layers.{qi}.codebook.embed_sum"] = rn(K, D, s=0.8 * (0.75 ** qi)) * usage[:, None]
+    return W

@@ -72,3 +72,28 @@ def test_voice_clone_prepends_ref_codes_and_cuts_proportionally():
     assert kw["non_streaming_mode"] is False and len(kw["ref_ids"]) == 2 and kw["voice_clone_prompt"]["icl_mode"] == [True, True]
     with pytest.raises(ValueError):
         m.generate_voice_clone("t")
+
+
+def test_tokenizer_audio_input_normalisation():
+    """inference/qwen3_tts_tokenizer.py:100-207 — ndarray(+sr) / list / base64 / data-URL / wav path; error behaviour."""
+    import base64
+    import io
+    import numpy as np
+    from scipy.io import wavfile
+    from qwen3_tts_b200.model import Qwen3TTSTokenizer as T
+    a = (np.sin(np.arange(16000) * 0.05) * 0.3).astype(np.float32)
+    out = T._normalize_audio_inputs([a, np.stack([a[:8000], a[:8000]], -1)], sr=16000)   # stereo -> mono, 16k -> 24k
+    assert [o.shape for o in out] == [(24000,), (12000,)] and out[0].dtype == np.float32
+    assert T._normalize_audio_inputs(a, sr=24000)[0] is not None and T._normalize_audio_inputs([], None) == []
+    buf = io.BytesIO()
+    wavfile.write(buf, 24000, (a * 32767).astype(np.int16))
+    b64 = base64.b64encode(buf.getvalue()).decode()
+    w = T._normalize_audio_inputs("data:audio/wav;base64," + b64, None)[0]
+    assert w.shape == a.shape and np.abs(w - a).max() < 1e-4
+    # raw base64 is only recognised when it has no '/' (the reference's heuristic, :100-107) -- same quirk here
+    assert T._is_probably_base64("A" * 300) and not T._is_probably_base64("A" * 300 + "/")
+    with pytest.raises(ValueError):
+        T._normalize_audio_inputs(a, None)
+    with pytest.raises(TypeError):
+        T._normalize_audio_inputs([a, "x.wav"], 24000)
+    assert T._is_url("https://example.com/a.wav") and not T._is_url("/tmp/a.wav")
