@@ -5,12 +5,13 @@
     SURVEY App. A.1) with plain PyTorch ops, then hands them to the fused AR engine (seam B) instead of
     `talker.generate`, and returns the per-sample code lists trimmed at the first EOS.
   * `Qwen3TTSModel`      == inference/qwen3_tts_model.py:54 (generate_custom_voice / voice_design / voice_clone).
-  * `Qwen3TTSTokenizer`  == inference/qwen3_tts_tokenizer.py:44 (decode(); encode() needs the Mimi encoder).
+  * `Qwen3TTSTokenizer`  == inference/qwen3_tts_tokenizer.py:44 (encode() on the fp32 codec encoder, decode()).
 
-No checkpoints/tokenizers exist offline, so construction takes the loaded state_dict + config + a `processor`
-callable (`processor(text=..., return_tensors="pt")["input_ids"]`, i.e. the HF Qwen2 tokenizer in production).
+Construction takes a state_dict + config + a `processor` callable (`processor(text=..., return_tensors="pt")
+["input_ids"]`); `from_pretrained` (checkpoint.py) builds those from a HF checkpoint directory like the reference's.
 """
 from dataclasses import dataclass
+import os
 from typing import Any, Dict, List, Optional, Tuple, Union
 
 import numpy as np
@@ -220,20 +221,42 @@ class Qwen3TTSTokenizer:
             from .codec_encoder import CodecEncoder
             self.encoder = CodecEncoder(encoder_cfg, encoder_weights, device=device)
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, device_map="cuda:0", max_frames=1024,
+                        with_encoder=True, **kwargs) -> "Qwen3TTSTokenizer":
+        """inference/qwen3_tts_tokenizer.py:63-99 — a local HF directory (config.json + safetensors of
+        Qwen3TTSTokenizerV2Model).  `device_map` names the CUDA device; `dtype` / `attn_implementation` kwargs of the
+        reference are accepted and ignored (the engines fix their own precisions: bf16 tensor-core decoder, fp32 encoder)."""
+        from . import checkpoint
+        d = checkpoint.resolve_dir(pretrained_model_name_or_path)
+        cfg_json = checkpoint.read_json(os.path.join(d, "config.json"))
+        mt = cfg_json.get("model_type", "qwen3_tts_tokenizer_12hz")
+        if mt != "qwen3_tts_tokenizer_12hz":
+            raise ValueError(f"unsupported tokenizer model_type {mt!r} (only the 12 Hz tokenizer is built)")
+        device = device_map if isinstance(device_map, (str, torch.device)) else "cuda:0"
+        ccfg, dec, ecfg, enc, rates = checkpoint.load_speech_tokenizer_checkpoint(d, device=device)
+        use_enc = with_encoder and len(enc) > 0
+        inst = cls(ccfg, dec, device=device, max_frames=max_frames, encoder_cfg=ecfg if use_enc else None,
+                   encoder_weights=enc if use_enc else None)
+        inst.rates = rates
+        return inst
+
+    rates = dict(input_sample_rate=24000, output_sample_rate=24000, decode_upsample_rate=None, encode_downsample_rate=None)
+
     def get_model_type(self):
         return "qwen3_tts_tokenizer_12hz"
 
     def get_input_sample_rate(self):
-        return 24000
+        return int(self.rates["input_sample_rate"])
 
     def get_output_sample_rate(self):
-        return 24000
+        return int(self.rates["output_sample_rate"])
 
     def get_encode_downsample_rate(self):
-        return self.config.total_upsample
+        return int(self.rates["encode_downsample_rate"] or self.config.total_upsample)
 
     def get_decode_upsample_rate(self):
-        return self.config.total_upsample
+        return int(self.rates["decode_upsample_rate"] or self.config.total_upsample)
 
     # ---- audio input normalisation (inference/qwen3_tts_tokenizer.py:100-207), host-only
     @staticmethod
@@ -358,6 +381,36 @@ class Qwen3TTSModel:
         self.processor = processor
         self.generate_defaults = generate_defaults or {}
         self.device = model.device
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, device_map="cuda:0", processor=None, max_batch=32,
+                        max_ctx=4096, codec_max_frames=1024, **kwargs) -> "Qwen3TTSModel":
+        """inference/qwen3_tts_model.py:82-121 + core/models/modeling_qwen3_tts.py:1843-1941: model weights, the
+        `speech_tokenizer/` sub-directory, `generation_config.json` (-> generate_defaults) and the text processor
+        (AutoTokenizer of the same directory, called like Qwen3TTSProcessor.__call__, processing_qwen3_tts.py:46-75).
+        `dtype` / `attn_implementation` are accepted and ignored; `processor=` overrides the tokenizer (tests)."""
+        from . import checkpoint
+        d = checkpoint.resolve_dir(pretrained_model_name_or_path)
+        device = device_map if isinstance(device_map, (str, torch.device)) else "cuda:0"
+        tcfg, W, meta, gen = checkpoint.load_tts_checkpoint(d, device=device)
+        core = Qwen3TTSForConditionalGenerationB200(
+            tcfg, W, device=device, spk_id=meta["spk_id"], spk_is_dialect=meta["spk_is_dialect"],
+            codec_language_id=meta["codec_language_id"], tts_model_type=meta["tts_model_type"] or "custom_voice",
+            tts_model_size=meta["tts_model_size"] or "1b7", max_batch=max_batch, max_ctx=max_ctx)
+        st_dir = os.path.join(d, "speech_tokenizer")
+        if not os.path.isdir(st_dir):
+            raise ValueError(f"{d}/speech_tokenizer not exists")
+        core.load_speech_tokenizer(Qwen3TTSTokenizer.from_pretrained(st_dir, device_map=device, max_frames=codec_max_frames))
+        core.load_generate_config(gen or {})
+        if processor is None:
+            from transformers import AutoTokenizer
+            tok = AutoTokenizer.from_pretrained(d)
+
+            def processor(text=None, **kw):
+                if text is None:
+                    raise ValueError("You need to specify either a `text` input to process.")
+                return tok(text if isinstance(text, list) else [text], **kw)
+        return cls(model=core, processor=processor, generate_defaults=core.generate_config)
 
     # ---- helpers (:207-352)
     @staticmethod

@@ -57,3 +57,74 @@ def run_engine_forced(eng, embs, trail, pad, sp_pkg, forced: np.ndarray, dev):
     prog = eng.progress()
     eng.set_debug(None, 0, None, None)
     return codes.cpu().numpy(), tl.cpu().numpy(), cl.cpu().numpy(), prog
+
+
+# ---------------------------------------------------------------------------------------------- synthetic HF checkpoints
+def tiny_checkpoint_configs():
+    """config.json dictionaries (reference format: core/models/configuration_qwen3_tts.py,
+    core/tokenizer_12hz/configuration_qwen3_tts_tokenizer_v2.py) for a tiny model matching synthetic.cfg_tiny()."""
+    talker = dict(vocab_size=3072, hidden_size=256, intermediate_size=512, num_hidden_layers=3, num_attention_heads=4,
+                  num_key_value_heads=2, head_dim=128, rms_norm_eps=1e-6, rope_theta=1e6,
+                  rope_scaling=dict(mrope_section=[24, 20, 20], interleaved=True, rope_type="default"),
+                  num_code_groups=16, text_hidden_size=256, text_vocab_size=1000, codec_eos_token_id=2150,
+                  codec_think_id=2154, codec_nothink_id=2155, codec_think_bos_id=2156, codec_think_eos_id=2157,
+                  codec_pad_id=2148, codec_bos_id=2149, spk_id={"Alice": 3000, "bob": 3001},
+                  spk_is_dialect={"Alice": False, "bob": False}, codec_language_id={"english": 2050, "chinese": 2055},
+                  code_predictor_config=dict(vocab_size=2048, hidden_size=128, intermediate_size=256, num_hidden_layers=2,
+                                             num_attention_heads=4, num_key_value_heads=2, head_dim=128,
+                                             rms_norm_eps=1e-6, rope_theta=1e4, num_code_groups=16))
+    top = dict(model_type="qwen3_tts", talker_config=talker, speaker_encoder_config={}, tokenizer_type="qwen3_tts_tokenizer_12hz",
+               tts_model_size="1b7", tts_model_type="custom_voice", tts_pad_token_id=996, tts_bos_token_id=997,
+               tts_eos_token_id=998)
+    tok = dict(model_type="qwen3_tts_tokenizer_12hz", encoder_valid_num_quantizers=16, input_sample_rate=24000,
+               output_sample_rate=24000, decode_upsample_rate=1920, encode_downsample_rate=1920,
+               decoder_config=dict(codebook_size=2048, codebook_dim=64, hidden_size=64, latent_dim=64,
+                                   num_attention_heads=4, num_key_value_heads=4, sliding_window=6, intermediate_size=96,
+                                   num_hidden_layers=2, num_quantizers=16, upsample_rates=[8, 5, 4, 3],
+                                   upsampling_ratios=[2, 2], decoder_dim=256, rms_norm_eps=1e-5, rope_theta=10000),
+               encoder_config=dict(model_type="mimi", num_filters=8, hidden_size=64, num_hidden_layers=2,
+                                   num_attention_heads=4, num_key_value_heads=4, head_dim=16, intermediate_size=96,
+                                   sliding_window=6, codebook_size=64, codebook_dim=32,
+                                   vector_quantization_hidden_dimension=32, upsample_groups=64))
+    gen = dict(do_sample=True, top_k=40, temperature=0.8, max_new_tokens=64)
+    return top, tok, gen
+
+
+def write_tiny_checkpoint(directory, device="cpu", sharded=False, seed=0):
+    """Write a complete synthetic checkpoint directory in the reference's on-disk format; returns what was written
+    (tts weights, decoder weights, encoder weights) for comparison."""
+    import json
+    import os
+    from safetensors.torch import save_file
+    import qwen3_tts_b200 as q
+    from qwen3_tts_b200 import synthetic
+    from qwen3_tts_b200.config import EncoderConfig
+    top, tok, gen = tiny_checkpoint_configs()
+    os.makedirs(os.path.join(directory, "speech_tokenizer"), exist_ok=True)
+    cfg = synthetic.cfg_tiny()
+    W = {k: v.cpu().contiguous() for k, v in synthetic.random_tts_weights(cfg, device=device, seed=seed, with_text=True).items()}
+    W["speaker_encoder.fc.weight"] = torch.zeros(4, 4, 1, dtype=torch.bfloat16)  # must be skipped by the loader
+    json.dump(top, open(os.path.join(directory, "config.json"), "w"))
+    json.dump(gen, open(os.path.join(directory, "generation_config.json"), "w"))
+    if sharded:
+        keys = sorted(W)
+        half = len(keys) // 2
+        parts = {"model-00001-of-00002.safetensors": keys[:half], "model-00002-of-00002.safetensors": keys[half:]}
+        for fn, ks in parts.items():
+            save_file({k: W[k] for k in ks}, os.path.join(directory, fn))
+        json.dump({"metadata": {}, "weight_map": {k: fn for fn, ks in parts.items() for k in ks}},
+                  open(os.path.join(directory, "model.safetensors.index.json"), "w"))
+    else:
+        save_file(W, os.path.join(directory, "model.safetensors"))
+    d = tok["decoder_config"]
+    ccfg = q.CodecConfig(codebook_size=d["codebook_size"], codebook_dim=d["codebook_dim"], hidden_size=d["hidden_size"],
+                         latent_dim=d["latent_dim"], num_heads=4, num_kv_heads=4, head_dim=16, sliding_window=6,
+                         intermediate_size=96, num_layers=2, decoder_dim=256)
+    DW = {k: v.cpu().float().contiguous() for k, v in synthetic.random_codec_weights(ccfg, device=device, seed=seed).items()}
+    ecfg = synthetic.cfg_encoder_tiny()
+    EW = {k: v.contiguous() for k, v in synthetic.random_encoder_weights(ecfg, seed=seed + 2).items()}
+    sd = {"decoder." + k: v for k, v in DW.items()}
+    sd.update({"encoder." + k: v for k, v in EW.items()})
+    json.dump(tok, open(os.path.join(directory, "speech_tokenizer", "config.json"), "w"))
+    save_file(sd, os.path.join(directory, "speech_tokenizer", "model.safetensors"))
+    return cfg, W, ccfg, DW, ecfg, EW
