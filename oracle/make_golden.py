@@ -10,6 +10,7 @@ import torch
 
 from . import codec as OC
 from . import mimi_encoder as OM
+from . import speaker_encoder as OS
 from . import ref_driver as R
 from . import talker as OT
 
@@ -125,13 +126,43 @@ def make_encoder():
     print("encoder_micro.npz", tuple(codes.shape))
 
 
+def make_speaker():
+    """Golden x-vectors from the reference's own Qwen3TTSSpeakerEncoder (modeling_qwen3_tts.py:300-393) and log-mels from
+    its mel_spectrogram (:396-448; the absent librosa filterbank is supplied by oracle.speaker_encoder)."""
+    from . import ref_shims
+    ref_shims.install()
+    from qwen_tts.core.models import modeling_qwen3_tts as RM
+    from qwen_tts.core.models.configuration_qwen3_tts import Qwen3TTSSpeakerEncoderConfig
+    cfg = OS.cfg_tiny_spk()
+    rc = Qwen3TTSSpeakerEncoderConfig(mel_dim=cfg.mel_dim, enc_dim=cfg.enc_dim, enc_channels=list(cfg.enc_channels),
+                                      enc_kernel_sizes=list(cfg.enc_kernel_sizes), enc_dilations=list(cfg.enc_dilations),
+                                      enc_attention_channels=cfg.enc_attention_channels,
+                                      enc_res2net_scale=cfg.enc_res2net_scale, enc_se_channels=cfg.enc_se_channels)
+    m = RM.Qwen3TTSSpeakerEncoder(rc).eval()
+    W = OS.random_weights(cfg, seed=19)
+    m.load_state_dict(W)
+    g = torch.Generator().manual_seed(6)
+    wav = (torch.randn(2, 6000, generator=g) * 0.1).clamp(-1, 1)
+    RM.librosa_mel_fn = lambda sr, n_fft, n_mels, fmin, fmax: OS.slaney_mel_filterbank(sr, n_fft, n_mels, fmin, fmax)
+    mel = RM.mel_spectrogram(wav, n_fft=1024, num_mels=cfg.mel_dim, sampling_rate=24000, hop_size=256, win_size=1024,
+                             fmin=0, fmax=12000)
+    with torch.no_grad():
+        emb = m(mel.transpose(1, 2))
+    blob = {f"W::{k}": v.numpy() for k, v in W.items()}
+    blob.update(wav=wav.numpy(), mel=mel.numpy(), emb=emb.numpy())
+    np.savez_compressed(os.path.join(OUT, "speaker_micro.npz"), **blob)
+    print("speaker_micro.npz", tuple(mel.shape), tuple(emb.shape))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     import sys
-    which = sys.argv[1:] or ["talker", "codec", "encoder"]
+    which = sys.argv[1:] or ["talker", "codec", "encoder", "speaker"]
     if "talker" in which:
         make_talker()
     if "codec" in which:
         make_codec()
     if "encoder" in which:
         make_encoder()
+    if "speaker" in which:
+        make_speaker()

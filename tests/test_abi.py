@@ -43,6 +43,16 @@ def test_engine_fails_loudly_without_gpu():
     h = ctypes.c_void_p()
     rc = lib.q3_engine_create(ctypes.byref(cfg), ctypes.byref(h))
     assert rc != 0 and b"CUDA" in lib.q3_last_error()
+    # the codec encoder and the Python wrappers refuse a CPU device as well (no fallback anywhere)
+    ec = _lib.CodecEncCfg()
+    ec.n_ratios, ec.head_dim, ec.num_heads, ec.hidden_size = 1, 16, 4, 64
+    ec.num_quantizers, ec.num_semantic_quantizers, ec.codebook_dim, ec.max_frames = 16, 1, 32, 16
+    rc = lib.q3_codec_enc_create(ctypes.byref(ec), ctypes.byref(h))
+    assert rc != 0 and b"CUDA" in lib.q3_last_error()
+    from qwen3_tts_b200 import synthetic
+    from qwen3_tts_b200.codec_encoder import CodecEncoder
+    with pytest.raises(RuntimeError):
+        CodecEncoder(synthetic.cfg_encoder_tiny(), {}, device="cpu")
 
 
 def test_sass_is_sm100a_with_tcgen05_tma():

@@ -48,3 +48,18 @@ def test_codec_decoder_against_golden_wav():
     assert torch.allclose(pre, wav[..., :5 * 1920], atol=1e-5)
     outs = OC.decode(W, cfg, torch.cat([codes.transpose(1, 2), -torch.ones(2, 3, 16, dtype=torch.long)], 1))
     assert [o.numel() for o in outs] == [9 * 1920] * 2
+
+
+def test_speaker_encoder_against_golden():
+    """x-vector path (voice cloning): log-mel front end and ECAPA-TDNN against vectors minted from the
+    reference's own modules."""
+    from oracle import speaker_encoder as OS
+    z = np.load(os.path.join(GOLD, "speaker_micro.npz"))
+    cfg = OS.cfg_tiny_spk()
+    W = _weights(z)
+    wav = torch.from_numpy(z["wav"])
+    mel = OS.mel_spectrogram(wav, num_mels=cfg.mel_dim)
+    assert mel.shape == z["mel"].shape and np.abs(mel.numpy() - z["mel"]).max() < 1e-4
+    emb = OS.speaker_encoder(W, cfg, torch.from_numpy(z["mel"]).transpose(1, 2))
+    assert np.abs(emb.numpy() - z["emb"]).max() < 1e-5
+    assert np.abs(OS.extract_speaker_embedding(W, cfg, wav[0]).numpy() - z["emb"][0]).max() < 1e-4

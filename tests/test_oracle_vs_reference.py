@@ -156,3 +156,34 @@ def test_codec_decoder_default_shapes_names():
         ref = m(codes)
     out = C.decoder_forward(W, cfg, codes)
     assert (out - ref).abs().max() < 5e-5
+
+
+@pytest.mark.parametrize("which", ["tiny", "default"])
+def test_speaker_encoder_and_mel_match_reference(which):
+    """ECAPA-TDNN x-vector (modeling_qwen3_tts.py:300-393) and the log-mel front end (:396-448).  The mel FILTERBANK is
+    librosa's (absent): the reference function is run with oracle.speaker_encoder's restatement patched in, so STFT,
+    magnitude, projection and log are pinned; the filterbank itself stays 'parity unpinned'."""
+    from oracle import ref_shims, speaker_encoder as S
+    ref_shims.install()
+    from qwen_tts.core.models import modeling_qwen3_tts as RM
+    from qwen_tts.core.models.configuration_qwen3_tts import Qwen3TTSSpeakerEncoderConfig
+    cfg = S.cfg_tiny_spk() if which == "tiny" else S.SpkEncCfg()
+    rc = Qwen3TTSSpeakerEncoderConfig(mel_dim=cfg.mel_dim, enc_dim=cfg.enc_dim, enc_channels=list(cfg.enc_channels),
+                                      enc_kernel_sizes=list(cfg.enc_kernel_sizes), enc_dilations=list(cfg.enc_dilations),
+                                      enc_attention_channels=cfg.enc_attention_channels,
+                                      enc_res2net_scale=cfg.enc_res2net_scale, enc_se_channels=cfg.enc_se_channels)
+    m = RM.Qwen3TTSSpeakerEncoder(rc).eval()
+    W = S.random_weights(cfg, seed=1)
+    m.load_state_dict(W)  # strict: every reference parameter has a counterpart
+    torch.manual_seed(0)
+    mels = torch.randn(2, 57, cfg.mel_dim)
+    with torch.no_grad():
+        ref = m(mels)
+    assert (ref - S.speaker_encoder(W, cfg, mels)).abs().max() < 1e-5
+    RM.librosa_mel_fn = lambda sr, n_fft, n_mels, fmin, fmax: S.slaney_mel_filterbank(sr, n_fft, n_mels, fmin, fmax)
+    y = (torch.randn(2, 9000) * 0.1).clamp(-1, 1)
+    refm = RM.mel_spectrogram(y, n_fft=1024, num_mels=cfg.mel_dim, sampling_rate=24000, hop_size=256, win_size=1024,
+                              fmin=0, fmax=12000)
+    assert (refm - S.mel_spectrogram(y, num_mels=cfg.mel_dim)).abs().max() < 1e-5
+    fb = S.slaney_mel_filterbank(24000, 1024, 128, 0, 12000)
+    assert fb.shape == (128, 513) and (fb >= 0).all() and (fb.sum(1) > 0).all()
