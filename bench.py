@@ -188,6 +188,33 @@ def config_block(args, lens, n_gpus):
             "l2": "per-step weight stream (>=3 GB) exceeds the 126 MB L2: no flush needed"}
 
 
+def codec_encoder_probe(dev):
+    """3 s of 24 kHz audio -> (16, 38) codes through Qwen3TTSTokenizer.encode's engine (fp32, default Mimi shapes,
+    seeded random weights), device-resident input, CUDA-event timed."""
+    import qwen3_tts_b200  # noqa: F401
+    from qwen3_tts_b200 import synthetic
+    from qwen3_tts_b200.codec_encoder import CodecEncoder
+    from qwen3_tts_b200.config import EncoderConfig
+    ecfg = EncoderConfig()
+    enc = CodecEncoder(ecfg, synthetic.random_encoder_weights(ecfg, seed=2), device=dev)
+    res = {"what": "codec encoder, 72000 samples (3 s) per row, fp32, ms per call", "launches": None}
+    for B in (1, 8):
+        wav = (torch.randn(B, 72000, device=dev) * 0.1).clamp(-1, 1)
+        for _ in range(2):
+            codes = enc.forward(wav)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            codes = enc.forward(wav)
+        e1.record()
+        torch.cuda.synchronize()
+        assert tuple(codes.shape) == (B, 16, 38)
+        res[f"ms_batch{B}"] = e0.elapsed_time(e1) / 5
+    res["launches"] = enc.last_launches()
+    return res
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -378,6 +405,12 @@ def main():
         out["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": ncores, "kind": "port",
                                "sample": f"prefill B={B} + {args.cpu_frames} frame-steps + codec decode of {args.cpu_frames} frames, "
                                          f"fp32, {ncores} threads, extrapolated to {N} frames", **det}
+    # ---- side measurement, never part of `value`: the codec ENCODER (BASELINE config 1's encode half)
+    if rank == 0 and world == 1:
+        try:
+            out["extras"] = {"codec_encoder": codec_encoder_probe(dev)}
+        except Exception as e:  # the headline line must survive whatever happens here
+            out["extras"] = {"codec_encoder": {"error": repr(e)[:200]}}
     if rank == 0:
         sys.stdout.flush()
         print(json.dumps(out), flush=True)

@@ -113,8 +113,9 @@ int q3_get_progress(q3_engine* e, int32_t* frames_done, int32_t* n_valid, int32_
 int q3_set_debug(q3_engine* e, const int32_t* forced_dev, int32_t n_frames, float* talker_logits_dev,
                  float* cp_logits_dev);
 
-/* Profiling hooks (profiles/ + bench --profile): prof_dev = uint64 [n_phases][2] globaltimer ns (phase end,
- * barrier end) written by CTA 0 for the first frame of each q3_decode; q3_describe_frame_program returns -n_phases
+/* Profiling hooks (tools/critical_path.py, tools/profile_frame.py): prof_dev = uint64 [n_phases][grid][8] %globaltimer
+ * ns written by thread 0 of EVERY CTA during the first frame of each q3_decode: [0] phase body end, [1] barrier passed,
+ * [2..5] inner marks of the phase body, [6] phase start, [7] staging mark; q3_describe_frame_program returns -n_phases
  * and fills kinds[i] = type*100 + stack*10 + epilogue. */
 int q3_set_profile(q3_engine* e, unsigned long long* prof_dev);
 int q3_describe_frame_program(q3_engine* e, int32_t* kinds, int32_t capacity);
