@@ -187,3 +187,47 @@ def test_speaker_encoder_and_mel_match_reference(which):
     assert (refm - S.mel_spectrogram(y, num_mels=cfg.mel_dim)).abs().max() < 1e-5
     fb = S.slaney_mel_filterbank(24000, 1024, 128, 0, 12000)
     assert fb.shape == (128, 513) and (fb >= 0).all() and (fb.sum(1) > 0).all()
+
+
+def _hf_processor_list(**gen_kwargs):
+    """The LogitsProcessorList HF itself builds for these generate() kwargs (GenerationMixin._get_logits_processor of
+    the installed transformers; the reference pins 4.57.3) — asked of a throw-away 1-layer GPT-2."""
+    from transformers import GenerationConfig, GPT2Config, GPT2LMHeadModel, LogitsProcessorList
+    m = GPT2LMHeadModel(GPT2Config(n_layer=1, n_head=1, n_embd=8, vocab_size=3072, n_positions=16))
+    gc = GenerationConfig(**gen_kwargs)
+    m._prepare_special_tokens(gc, kwargs_has_attention_mask=True, device="cpu")  # sets _eos_token_tensor (min_new_tokens needs it)
+    return m._get_logits_processor(generation_config=gc, input_ids_seq_length=0, encoder_input_ids=None,
+                                   prefix_allowed_tokens_fn=None, logits_processor=LogitsProcessorList(), device="cpu")
+
+
+def test_sampler_matches_hf_logits_processors():
+    """oracle/sampler.py::process_logits against the third-party processors the reference configures at
+    modeling_qwen3_tts.py:2044-2066 / :2272-2278 — both the ORDER HF applies them in and the formulas, on the talker's
+    settings (repetition penalty over generated ids, min_new_tokens=2, suppress [V-1024, V) \\ {eos}, T, top-k, top-p)."""
+    from oracle import sampler as OSm
+    V, eos = 3072, 2150
+    rng = np.random.default_rng(0)
+    suppress = [i for i in range(V - 1024, V) if i != eos]
+    for trial, (top_p, n_gen) in enumerate([(1.0, 0), (1.0, 1), (0.8, 5), (0.95, 40)]):
+        kw = dict(do_sample=True, top_k=50, top_p=top_p, temperature=0.9, repetition_penalty=1.05, min_new_tokens=2,
+                  eos_token_id=eos, suppress_tokens=suppress, max_new_tokens=100, pad_token_id=eos)
+        procs = _hf_processor_list(**kw)
+        names = [type(p).__name__ for p in procs]
+        want = ["RepetitionPenaltyLogitsProcessor", "MinNewTokensLengthLogitsProcessor", "SuppressTokensLogitsProcessor",
+                "TemperatureLogitsWarper", "TopKLogitsWarper"] + (["TopPLogitsWarper"] if top_p < 1.0 else [])
+        assert names == want, names
+        logits = (rng.standard_normal(V) * 3).astype(np.float32)
+        gen = rng.integers(0, 2048, size=n_gen)
+        ids = torch.from_numpy(gen.astype(np.int64))[None]          # HF's input_ids = generated ids only (inputs_embeds prompt)
+        hf = procs(ids, torch.from_numpy(logits)[None].clone())[0].numpy()
+        mine = OSm.process_logits(logits, generated_ids=list(gen), repetition_penalty=1.05, min_new_tokens=2,
+                                  eos_token_id=eos, suppress_lo=V - 1024, suppress_hi=V, do_sample=True, temperature=0.9,
+                                  top_k=50, top_p=top_p)
+        assert np.array_equal(np.isfinite(hf), np.isfinite(mine)), f"trial {trial}: kept sets differ"
+        keep = np.isfinite(hf)
+        assert np.abs(hf[keep] - mine[keep]).max() < 1e-6
+    # greedy: no warpers, same three processors
+    names = [type(p).__name__ for p in _hf_processor_list(do_sample=False, repetition_penalty=1.05, min_new_tokens=2,
+                                                           eos_token_id=eos, suppress_tokens=suppress, max_new_tokens=9,
+                                                           pad_token_id=eos)]
+    assert names == ["RepetitionPenaltyLogitsProcessor", "MinNewTokensLengthLogitsProcessor", "SuppressTokensLogitsProcessor"]
