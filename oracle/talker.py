@@ -236,6 +236,51 @@ def talker_logits_processors(cfg: TTSCfg, sp: SamplingCfg):
                 do_sample=sp.do_sample, temperature=sp.temperature, top_k=sp.top_k, top_p=sp.top_p)
 
 
+def hf_sample_loop(first_logits, step_fn, B, lp, do_sample, seed, max_new_tokens, eos, forced_tok=None, on_logits=None):
+    """The control flow of HF `GenerationMixin._sample` as the reference drives it (talker.generate at
+    modeling_qwen3_tts.py:2272-2278; third-party transformers==4.57.3), separated from the model so that it can be
+    pinned against the real `_sample` with any model (tests/test_oracle_vs_reference.py):
+      scores = processors(generated ids of the row, logits); token = argmax | sample;
+      rows that already emitted EOS keep stepping but receive pad_token_id (= eos);
+      a row finishes on EOS; the loop ends when every row has finished or max_new_tokens tokens exist.
+    first_logits: (B, V) fp32 from the prefill; step_fn(tokens (B,), step) -> next (B, V) logits.
+    Returns (list of (B,) token tensors, number of step_fn calls)."""
+    generated = [[] for _ in range(B)]
+    finished = [False] * B
+
+    def pick(logits, idx):
+        tok = torch.zeros(B, dtype=torch.int64)
+        for b in range(B):
+            s = S.process_logits(logits[b].numpy(), generated_ids=generated[b], **lp)
+            u = philox.uniform(seed, b, idx, 0) if do_sample else None
+            t, _ = S.sample_from_scores(s, do_sample=do_sample, u=u)
+            tok[b] = eos if finished[b] else t  # HF pads finished rows with pad_token_id (= eos)
+        f = forced_tok(idx) if forced_tok is not None else None
+        return tok if f is None else f
+
+    def update(tok):
+        for b in range(B):
+            if not finished[b]:
+                generated[b].append(int(tok[b]))
+                finished[b] = int(tok[b]) == eos
+
+    if on_logits is not None:
+        on_logits(first_logits)
+    tok = pick(first_logits, 0)
+    update(tok)
+    tokens = [tok]
+    step = 0  # == generation_step of the reference after prefill (:1666,1741)
+    while not all(finished) and len(tokens) < max_new_tokens:
+        logits = step_fn(tok, step)
+        if on_logits is not None:
+            on_logits(logits)
+        step += 1
+        tok = pick(logits, step)
+        update(tok)
+        tokens.append(tok)
+    return tokens, step
+
+
 def generate(W, cfg: TTSCfg, inputs_embeds: List[torch.Tensor], trailing_text: List[torch.Tensor],
              tts_pad_embed: torch.Tensor, sp: SamplingCfg, record_logits=False,
              forced_codes: Optional[np.ndarray] = None) -> GenResult:
@@ -274,37 +319,25 @@ def generate(W, cfg: TTSCfg, inputs_embeds: List[torch.Tensor], trailing_text: L
     lp = talker_logits_processors(cfg, sp)
     if sp.suppress_eos:
         lp = dict(lp, min_new_tokens=1 << 30)
-    generated = [[] for _ in range(B)]
-    finished = [False] * B
     frames = []  # list of (B,16)
     eos = cfg.codec_eos_token_id
+    state = dict(past_hidden=past_hidden, valid_kv=valid.clone())
 
-    def sample_c0(logits, frame_idx):
-        c0 = torch.zeros(B, dtype=torch.int64)
-        for b in range(B):
-            s = S.process_logits(logits[b].numpy(), generated_ids=generated[b], **lp)
-            u = philox.uniform(sp.seed, b, frame_idx, 0) if sp.do_sample else None
-            tok, _ = S.sample_from_scores(s, do_sample=sp.do_sample, u=u)
-            c0[b] = eos if finished[b] else tok  # HF pads finished rows with pad_token_id (= eos)
-        return c0
+    def on_logits(lg):
+        if record_logits:
+            rec.setdefault("talker_logits", []).append(lg.numpy().copy())
 
-    if record_logits:
-        rec.setdefault("talker_logits", []).append(logits.numpy().copy())
-    c0 = sample_c0(logits, 0)
-    if forced_codes is not None and forced_codes.shape[1] > 0:
-        c0 = torch.from_numpy(forced_codes[:, 0, 0].astype(np.int64))
-    for b in range(B):
-        generated[b].append(int(c0[b]))
-        finished[b] = finished[b] or int(c0[b]) == eos
-    step = 0  # == generation_step of the reference after prefill (:1666,1741)
-    n_tokens = 1
-    valid_kv = valid.clone()
-    while not all(finished) and n_tokens < sp.max_new_tokens:
-        # --- decode step: emits the 16 codes of frame `step` (:1669-1692)
+    def forced_c0(idx):
+        if forced_codes is not None and idx < forced_codes.shape[1]:
+            return torch.from_numpy(forced_codes[:, idx, 0].astype(np.int64))
+        return None
+
+    def step_fn(c0, step):
+        """One decode step: emits the 16 codes of frame `step` (:1669-1692) and returns the next codebook-0 logits."""
         forced_rest = None
         if forced_codes is not None and step < forced_codes.shape[1]:
             forced_rest = forced_codes[:, step, 1:].astype(np.int64)
-        rest = code_predictor_frame(W, cfg, past_hidden, c0, sp, step, forced=forced_rest,
+        rest = code_predictor_frame(W, cfg, state["past_hidden"], c0, sp, step, forced=forced_rest,
                                     record=rec if record_logits else None)
         codes16 = torch.cat((c0[:, None], rest), dim=1)
         frames.append(codes16)
@@ -315,23 +348,14 @@ def generate(W, cfg: TTSCfg, inputs_embeds: List[torch.Tensor], trailing_text: L
             xe = xe + tts_pad
         # positions (:1699-1711): cache_position + rope_deltas = len_i + step
         posd = (lens + step)[:, None]
-        valid_kv = torch.cat((valid_kv, torch.ones(B, 1, dtype=torch.bool)), dim=1)
-        ctx = valid_kv.shape[1]
-        mask = causal_mask(valid_kv, torch.tensor([ctx - 1]), dt)
-        h = stack_forward(W, "talker.model", cfg.talker, xe, posd, mask, cache)
-        past_hidden = h[:, -1:, :]
-        logits = F.linear(past_hidden[:, 0], W["talker.codec_head.weight"]).to(torch.float32)
-        if record_logits:
-            rec["talker_logits"].append(logits.numpy().copy())
-        step += 1
-        c0 = sample_c0(logits, step)
-        if forced_codes is not None and step < forced_codes.shape[1]:
-            c0 = torch.from_numpy(forced_codes[:, step, 0].astype(np.int64))
-        for b in range(B):
-            if not finished[b]:
-                generated[b].append(int(c0[b]))
-                finished[b] = int(c0[b]) == eos
-        n_tokens += 1
+        state["valid_kv"] = torch.cat((state["valid_kv"], torch.ones(B, 1, dtype=torch.bool)), dim=1)
+        ctx = state["valid_kv"].shape[1]
+        m = causal_mask(state["valid_kv"], torch.tensor([ctx - 1]), dt)
+        hh = stack_forward(W, "talker.model", cfg.talker, xe, posd, m, cache)
+        state["past_hidden"] = hh[:, -1:, :]
+        return F.linear(state["past_hidden"][:, 0], W["talker.codec_head.weight"]).to(torch.float32)
+
+    _, step = hf_sample_loop(logits, step_fn, B, lp, sp.do_sample, sp.seed, sp.max_new_tokens, eos, forced_c0, on_logits)
     # post-trim (:2280-2290)
     out = []
     if frames:
