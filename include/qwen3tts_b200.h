@@ -196,6 +196,37 @@ int q3_codec_enc_last_launch_count(q3_codec_enc* e);
  * transformer layer, downsample) of the next encode into dst; stage < 0 clears all captures. */
 int q3_codec_enc_debug_capture(q3_codec_enc* e, int32_t stage, float* dst_dev, int64_t capacity);
 
+/* ---------------------------------------------------------------- speaker x-vector (voice cloning)
+ * Replaces Qwen3TTSForConditionalGeneration.extract_speaker_embedding (core/models/modeling_qwen3_tts.py:1941-1954):
+ * mel_spectrogram (:396-448) + Qwen3TTSSpeakerEncoder.forward (:371-393).  fp32.  NOT YET RUN ON HARDWARE (written
+ * after round 1's GPU budget was spent; see csrc/speaker_encoder.cu). */
+typedef struct {
+  int32_t mel_dim, enc_dim;                 /* Qwen3TTSSpeakerEncoderConfig (configuration_qwen3_tts.py:47-57) */
+  int32_t n_blocks;                         /* len(enc_channels) */
+  int32_t channels[8], kernel_sizes[8], dilations[8];
+  int32_t attention_channels, res2net_scale, se_channels;
+  int32_t n_fft, hop, win;                  /* 1024, 256, 1024 at the reference call site (:1943-1951) */
+  int32_t device;
+} q3_spk_cfg;
+typedef struct q3_spk q3_spk;
+
+int q3_spk_create(const q3_spk_cfg* cfg, q3_spk** out);
+void q3_spk_destroy(q3_spk* e);
+/* fp32 device tensors: the reference's own `speaker_encoder.` state_dict names with the prefix stripped
+ * ("blocks.0.conv.weight", "blocks.<i>.tdnn1.conv.weight", "blocks.<i>.res2net_block.blocks.<j>.conv.weight",
+ * "blocks.<i>.se_block.conv1.weight", "mfa.conv.weight", "asp.tdnn.conv.weight", "asp.conv.weight", "fc.weight", and
+ * the matching ".bias"), plus the host-computed front-end tables "mel.window" [n_fft] (Hann), "mel.cos" / "mel.sin"
+ * [n_fft] = cos/sin(2*pi*j/n_fft), "mel.fbT" [n_fft/2+1][mel_dim] (librosa-style Slaney filterbank, transposed). */
+int q3_spk_load_tensor(q3_spk* e, const char* name, const float* dev, const int64_t* shape, int32_t ndim);
+int q3_spk_finalize(q3_spk* e);
+int q3_spk_frames(q3_spk* e, int32_t T);    /* STFT frames of a T-sample waveform */
+/* wav fp32 [B][T] -> log-mel fp32 [B][mel_dim][frames] */
+int q3_spk_mel(q3_spk* e, const float* wav_dev, int32_t B, int32_t T, float* mel_dev, void* stream);
+/* wav fp32 [B][T] (or, when mel_dev != NULL, a ready mel [B][mel_dim][frames]) -> emb fp32 [B][enc_dim] */
+int q3_spk_embed(q3_spk* e, const float* wav_dev, int32_t B, int32_t T, const float* mel_dev, int32_t frames,
+                 float* emb_dev, void* stream);
+int q3_spk_last_launch_count(q3_spk* e);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,13 @@ class CodecEncCfg(C.Structure):
                                           "downsample_stride", "max_frames", "device")]
 
 
+class SpkCfg(C.Structure):
+    _fields_ = [("mel_dim", C.c_int32), ("enc_dim", C.c_int32), ("n_blocks", C.c_int32), ("channels", C.c_int32 * 8),
+                ("kernel_sizes", C.c_int32 * 8), ("dilations", C.c_int32 * 8), ("attention_channels", C.c_int32),
+                ("res2net_scale", C.c_int32), ("se_channels", C.c_int32), ("n_fft", C.c_int32), ("hop", C.c_int32),
+                ("win", C.c_int32), ("device", C.c_int32)]
+
+
 # every symbol include/qwen3tts_b200.h declares (tests/test_abi.py checks the header against this list)
 AR_SYMBOLS = ["q3_abi_version", "q3_last_error", "q3_engine_create", "q3_engine_destroy", "q3_engine_load_tensor",
               "q3_engine_finalize", "q3_prefill", "q3_decode", "q3_get_progress", "q3_set_debug",
@@ -58,7 +65,9 @@ CODEC_SYMBOLS = ["q3_codec_create", "q3_codec_destroy", "q3_codec_load_tensor", 
                  "q3_codec_forward", "q3_codec_total_upsample", "q3_codec_last_launch_count",
                  "q3_codec_enc_create", "q3_codec_enc_destroy", "q3_codec_enc_load_tensor", "q3_codec_enc_finalize",
                  "q3_codec_enc_encode", "q3_codec_enc_frames", "q3_codec_enc_hop", "q3_codec_enc_last_launch_count",
-                 "q3_codec_enc_debug_capture"]
+                 "q3_codec_enc_debug_capture",
+                 "q3_spk_create", "q3_spk_destroy", "q3_spk_load_tensor", "q3_spk_finalize", "q3_spk_frames", "q3_spk_mel",
+                 "q3_spk_embed", "q3_spk_last_launch_count"]
 
 _lib = None
 
@@ -116,6 +125,15 @@ def load():
         lib.q3_codec_enc_hop.argtypes = [vp]
         lib.q3_codec_enc_last_launch_count.argtypes = [vp]
         lib.q3_codec_enc_debug_capture.argtypes = [vp, i32, vp, i64]
+        lib.q3_spk_create.argtypes = [C.POINTER(SpkCfg), C.POINTER(vp)]
+        lib.q3_spk_destroy.argtypes = [vp]
+        lib.q3_spk_destroy.restype = None
+        lib.q3_spk_load_tensor.argtypes = [vp, C.c_char_p, vp, C.POINTER(i64), i32]
+        lib.q3_spk_finalize.argtypes = [vp]
+        lib.q3_spk_frames.argtypes = [vp, i32]
+        lib.q3_spk_mel.argtypes = [vp, vp, i32, i32, vp, vp]
+        lib.q3_spk_embed.argtypes = [vp, vp, i32, i32, vp, i32, vp, vp]
+        lib.q3_spk_last_launch_count.argtypes = [vp]
     _lib = lib
     return lib
 

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libqwen3tts_b200.so")
-SOURCES = ["ar_engine.cu", "codec_engine.cu", "codec_encoder.cu", "gemm_sm100.cu"]
+SOURCES = ["ar_engine.cu", "codec_engine.cu", "codec_encoder.cu", "speaker_encoder.cu", "gemm_sm100.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-cudart", "shared", "--expt-relaxed-constexpr"]
 

@@ -16,7 +16,7 @@ from typing import Dict, Optional, Tuple
 
 import torch
 
-from .config import CodecConfig, EncoderConfig, TTSConfig
+from .config import CodecConfig, EncoderConfig, SpeakerEncoderConfig, TTSConfig
 
 # core/models/configuration_qwen3_tts.py:187-212 (Qwen3TTSTalkerCodePredictorConfig.__init__ defaults)
 CODE_PREDICTOR_DEFAULTS = dict(vocab_size=2048, hidden_size=1024, intermediate_size=3072, num_hidden_layers=5,
@@ -103,15 +103,22 @@ def tts_config_from_dict(cfg: dict):
     tcfg = TTSConfig.from_hf(top)
     meta = dict(spk_id=talker.spk_id or {}, spk_is_dialect=talker.spk_is_dialect or {},
                 codec_language_id=talker.codec_language_id or {}, tts_model_type=top.tts_model_type,
-                tts_model_size=top.tts_model_size, tokenizer_type=top.tokenizer_type)
+                tts_model_size=top.tts_model_size, tokenizer_type=top.tokenizer_type,
+                speaker_encoder_config=SpeakerEncoderConfig.from_dict(cfg.get("speaker_encoder_config")))
     return tcfg, meta
 
 
 def load_tts_checkpoint(directory: str, device="cuda:0", dtype=torch.bfloat16):
     """-> (TTSConfig, weights keyed by the reference state_dict names, meta, generate_config | None).
-    `speaker_encoder.*` tensors are skipped: the speaker encoder is not built yet."""
+    Base checkpoints also carry `speaker_encoder.*` (modeling_qwen3_tts.py:1822-1825): returned fp32, prefix stripped,
+    in meta["speaker_encoder_weights"] (empty for the other model types)."""
     tcfg, meta = tts_config_from_dict(read_json(os.path.join(directory, "config.json")))
     W = read_state_dict(directory, device=device, dtype=dtype, prefixes=("talker.",))
+    spk = {}
+    if meta["tts_model_type"] == "base":
+        spk = {k[len("speaker_encoder."):]: v for k, v in
+               read_state_dict(directory, device=device, dtype=torch.float32, prefixes=("speaker_encoder.",)).items()}
+    meta["speaker_encoder_weights"] = spk
     gen = None
     gpath = os.path.join(directory, "generation_config.json")
     if os.path.exists(gpath):

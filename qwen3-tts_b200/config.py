@@ -160,3 +160,30 @@ class EncoderConfig:
                              float(mc.norm_eps), mc.codebook_size, mc.codebook_dim, mc.num_semantic_quantizers,
                              int(valid_num_quantizers), int(round(mc.encodec_frame_rate / mc.frame_rate)),
                              mc.max_position_embeddings, int(encode_downsample_rate))
+
+
+@dataclass
+class SpeakerEncoderConfig:
+    """Qwen3TTSSpeakerEncoderConfig defaults (core/models/configuration_qwen3_tts.py:47-57) + the mel front-end constants
+    hard-coded at the reference call site (modeling_qwen3_tts.py:1943-1951)."""
+    mel_dim: int = 128
+    enc_dim: int = 1024
+    enc_channels: Tuple[int, ...] = (512, 512, 512, 512, 1536)
+    enc_kernel_sizes: Tuple[int, ...] = (5, 3, 3, 3, 1)
+    enc_dilations: Tuple[int, ...] = (1, 2, 3, 4, 1)
+    enc_attention_channels: int = 128
+    enc_res2net_scale: int = 8
+    enc_se_channels: int = 128
+    sample_rate: int = 24000
+    n_fft: int = 1024
+    hop_size: int = 256
+    win_size: int = 1024
+    fmin: float = 0.0
+    fmax: float = 12000.0
+
+    @staticmethod
+    def from_dict(d):
+        d = d or {}
+        base = SpeakerEncoderConfig()
+        kw = {k: (tuple(v) if isinstance(v, (list, tuple)) else v) for k, v in d.items() if hasattr(base, k)}
+        return SpeakerEncoderConfig(**kw)

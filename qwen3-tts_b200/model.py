@@ -53,6 +53,9 @@ class Qwen3TTSForConditionalGenerationB200:
                               for j in range(cfg.num_code_groups - 1)]
         self.engine = engine or AREngine(cfg, weights, device=device, max_batch=max_batch, max_ctx=max_ctx)
         self.speech_tokenizer = None
+        self.speaker_encoder = None            # SpeakerEncoder (Base checkpoints), see load_speaker_encoder
+        self.speaker_encoder_sample_rate = 24000
+        self.tokenizer_type = None
         self.generate_config = None
         self.supported_speakers = self.spk_id.keys()
         self.supported_languages = ["auto"] + [k for k in self.codec_language_id if "dialect" not in k]
@@ -71,6 +74,18 @@ class Qwen3TTSForConditionalGenerationB200:
 
     def load_generate_config(self, generate_config):
         self.generate_config = generate_config
+
+    def load_speaker_encoder(self, speaker_encoder):
+        self.speaker_encoder = speaker_encoder
+        self.speaker_encoder_sample_rate = int(speaker_encoder.cfg.sample_rate)
+
+    def extract_speaker_embedding(self, audio: np.ndarray, sr: int) -> torch.Tensor:
+        """:1941-1954 — 24 kHz mono waveform -> (enc_dim,) x-vector in the model dtype."""
+        assert sr == 24000, "Only support 24kHz audio"
+        if self.speaker_encoder is None:
+            raise RuntimeError("this model was built without speaker-encoder weights (only Base checkpoints carry them)")
+        emb = self.speaker_encoder.embed_waveform(torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32))[None])[0]
+        return emb.to(self.dtype)
 
     def get_supported_speakers(self):
         return self.supported_speakers
@@ -402,6 +417,10 @@ class Qwen3TTSModel:
             raise ValueError(f"{d}/speech_tokenizer not exists")
         core.load_speech_tokenizer(Qwen3TTSTokenizer.from_pretrained(st_dir, device_map=device, max_frames=codec_max_frames))
         core.load_generate_config(gen or {})
+        core.tokenizer_type = meta.get("tokenizer_type")
+        if meta.get("speaker_encoder_weights"):
+            from .speaker_encoder import SpeakerEncoder
+            core.load_speaker_encoder(SpeakerEncoder(meta["speaker_encoder_config"], meta["speaker_encoder_weights"], device=device))
         if processor is None:
             from transformers import AutoTokenizer
             tok = AutoTokenizer.from_pretrained(d)
@@ -534,10 +553,66 @@ class Qwen3TTSModel:
                                        non_streaming_mode=non_streaming_mode, **self._merge_generate_kwargs(**kwargs))
         return self._decode(codes)
 
-    # ---- :355-458 — needs the codec ENCODER and the speaker encoder ("next" rows): prompts must be supplied
-    def create_voice_clone_prompt(self, ref_audio, ref_text=None, x_vector_only_mode=False):
-        raise NotImplementedError("create_voice_clone_prompt needs the Mimi codec encoder and the ECAPA speaker encoder "
-                                  "(SURVEY §8f rows 1/3); build VoiceClonePromptItem with the reference and pass it in")
+    # ---- :207-257 — str (path / URL / base64) | (ndarray, sr) | list of those -> [(float32 mono waveform, sr)]
+    def _normalize_audio_inputs(self, audios) -> List[Tuple[np.ndarray, int]]:
+        items = audios if isinstance(audios, list) else [audios]
+        out: List[Tuple[np.ndarray, int]] = []
+        for a in items:
+            if isinstance(a, str):
+                from scipy.io import wavfile
+                import base64
+                import io
+                if Qwen3TTSTokenizer._is_url(a):
+                    import urllib.request
+                    with urllib.request.urlopen(a) as resp:
+                        src = io.BytesIO(resp.read())
+                elif Qwen3TTSTokenizer._is_probably_base64(a):
+                    b64 = a.split(",", 1)[1] if ("," in a and a.strip().startswith("data:")) else a
+                    src = io.BytesIO(base64.b64decode(b64))
+                else:
+                    src = a
+                sr, audio = wavfile.read(src)
+                if audio.dtype.kind == "i":
+                    audio = audio.astype(np.float32) / float(np.iinfo(audio.dtype).max + 1)
+                elif audio.dtype.kind == "u":
+                    audio = (audio.astype(np.float32) - 128.0) / 128.0
+                out.append((audio.astype(np.float32), int(sr)))
+            elif isinstance(a, tuple) and len(a) == 2 and isinstance(a[0], np.ndarray):
+                out.append((a[0].astype(np.float32), int(a[1])))
+            elif isinstance(a, np.ndarray):
+                raise ValueError("For numpy waveform input, pass a tuple (audio, sr).")
+            else:
+                raise TypeError(f"Unsupported audio input type: {type(a)}")
+        return [(np.mean(w, axis=-1).astype(np.float32) if w.ndim > 1 else w, sr) for w, sr in out]
+
+    # ---- :355-458
+    def create_voice_clone_prompt(self, ref_audio, ref_text=None, x_vector_only_mode=False) -> List[VoiceClonePromptItem]:
+        if self.model.tts_model_type != "base":
+            raise ValueError(f"model with \ntokenizer_type: {getattr(self.model, 'tokenizer_type', None)}\n"
+                             f"tts_model_size: {self.model.tts_model_size}\ntts_model_type: {self.model.tts_model_type}\n"
+                             "does not support create_voice_clone_prompt, Please check Model Card or Readme for more details.")
+        audios = self._ensure_list(ref_audio)
+        texts = self._ensure_list(ref_text) if isinstance(ref_text, list) else [ref_text] * len(audios)
+        xvecs = self._ensure_list(x_vector_only_mode) if isinstance(x_vector_only_mode, list) else [x_vector_only_mode] * len(audios)
+        if len(texts) != len(audios) or len(xvecs) != len(audios):
+            raise ValueError(f"Batch size mismatch: ref_audio={len(audios)}, ref_text={len(texts)}, x_vector_only_mode={len(xvecs)}")
+        normalized = self._normalize_audio_inputs(audios)
+        srs = [sr for _, sr in normalized]
+        tok = self.model.speech_tokenizer
+        if len(set(srs)) == 1:
+            ref_codes = tok.encode([w for w, _ in normalized], sr=srs[0]).audio_codes
+        else:
+            ref_codes = [tok.encode(w, sr=sr).audio_codes[0] for w, sr in normalized]
+        items: List[VoiceClonePromptItem] = []
+        for i, ((wav, sr), code, rtext, xv) in enumerate(zip(normalized, ref_codes, texts, xvecs)):
+            if not xv and (rtext is None or rtext == ""):
+                raise ValueError(f"ref_text is required when x_vector_only_mode=False (ICL mode). Bad index={i}")
+            target = int(self.model.speaker_encoder_sample_rate)
+            w24 = wav if sr == target else Qwen3TTSTokenizer._resample(wav, sr, target)
+            emb = self.model.extract_speaker_embedding(audio=w24, sr=target)
+            items.append(VoiceClonePromptItem(ref_code=None if xv else code, ref_spk_embedding=emb,
+                                              x_vector_only_mode=bool(xv), icl_mode=bool(not xv), ref_text=rtext))
+        return items
 
     @staticmethod
     def _prompt_items_to_voice_clone_prompt(items: List[VoiceClonePromptItem]) -> Dict[str, Any]:

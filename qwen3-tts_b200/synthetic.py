@@ -210,3 +210,36 @@ def random_encoder_weights(cfg, seed=0):
             W[p + f"layers.{qi}.codebook.cluster_usage"] = usage
             W[p + f"layers.{qi}.codebook.embed_sum"] = rn(K, D, s=0.8 * (0.75 ** qi)) * usage[:, None]
     return W
+
+
+def cfg_speaker_encoder_tiny():
+    from .config import SpeakerEncoderConfig
+    return SpeakerEncoderConfig(mel_dim=16, enc_dim=24, enc_channels=(32, 32, 32, 64), enc_kernel_sizes=(5, 3, 3, 1),
+                                enc_dilations=(1, 2, 3, 1), enc_attention_channels=8, enc_res2net_scale=4, enc_se_channels=8)
+
+
+def random_speaker_encoder_weights(cfg, seed=0):
+    """Seeded fp32 weights under the reference's `speaker_encoder.` state_dict names (prefix stripped), CPU tensors."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    W = {}
+
+    def conv(p, cin, cout, k):
+        W[p + ".weight"] = torch.randn(cout, cin, k, generator=g) / math.sqrt(cin * k)
+        W[p + ".bias"] = torch.randn(cout, generator=g) * 0.05
+
+    ch, ks, s = cfg.enc_channels, cfg.enc_kernel_sizes, cfg.enc_res2net_scale
+    conv("blocks.0.conv", cfg.mel_dim, ch[0], ks[0])
+    for i in range(1, len(ch) - 1):
+        p = f"blocks.{i}"
+        conv(p + ".tdnn1.conv", ch[i - 1], ch[i], 1)
+        for j in range(s - 1):
+            conv(f"{p}.res2net_block.blocks.{j}.conv", ch[i] // s, ch[i] // s, ks[i])
+        conv(p + ".tdnn2.conv", ch[i], ch[i], 1)
+        conv(p + ".se_block.conv1", ch[i], cfg.enc_se_channels, 1)
+        conv(p + ".se_block.conv2", cfg.enc_se_channels, ch[i], 1)
+    conv("mfa.conv", ch[-1], ch[-1], ks[-1])
+    conv("asp.tdnn.conv", ch[-1] * 3, cfg.enc_attention_channels, 1)
+    conv("asp.conv", cfg.enc_attention_channels, ch[-1], 1)
+    conv("fc", ch[-1] * 2, cfg.enc_dim, 1)
+    return W

@@ -90,7 +90,7 @@ def tiny_checkpoint_configs():
     return top, tok, gen
 
 
-def write_tiny_checkpoint(directory, device="cpu", sharded=False, seed=0):
+def write_tiny_checkpoint(directory, device="cpu", sharded=False, seed=0, model_type="custom_voice"):
     """Write a complete synthetic checkpoint directory in the reference's on-disk format; returns what was written
     (tts weights, decoder weights, encoder weights) for comparison."""
     import json
@@ -103,7 +103,17 @@ def write_tiny_checkpoint(directory, device="cpu", sharded=False, seed=0):
     os.makedirs(os.path.join(directory, "speech_tokenizer"), exist_ok=True)
     cfg = synthetic.cfg_tiny()
     W = {k: v.cpu().contiguous() for k, v in synthetic.random_tts_weights(cfg, device=device, seed=seed, with_text=True).items()}
-    W["speaker_encoder.fc.weight"] = torch.zeros(4, 4, 1, dtype=torch.bfloat16)  # must be skipped by the loader
+    if model_type == "base":   # Base checkpoints carry the ECAPA speaker encoder (modeling_qwen3_tts.py:1822-1825)
+        scfg = synthetic.cfg_speaker_encoder_tiny()
+        top = dict(top, tts_model_type="base",
+                   speaker_encoder_config=dict(mel_dim=scfg.mel_dim, enc_dim=scfg.enc_dim, enc_channels=list(scfg.enc_channels),
+                                               enc_kernel_sizes=list(scfg.enc_kernel_sizes), enc_dilations=list(scfg.enc_dilations),
+                                               enc_attention_channels=scfg.enc_attention_channels,
+                                               enc_res2net_scale=scfg.enc_res2net_scale, enc_se_channels=scfg.enc_se_channels))
+        for k, v in synthetic.random_speaker_encoder_weights(scfg, seed=seed + 3).items():
+            W["speaker_encoder." + k] = v.to(torch.bfloat16).contiguous()
+    else:
+        W["speaker_encoder.fc.weight"] = torch.zeros(4, 4, 1, dtype=torch.bfloat16)  # must be skipped by the loader
     json.dump(top, open(os.path.join(directory, "config.json"), "w"))
     json.dump(gen, open(os.path.join(directory, "generation_config.json"), "w"))
     if sharded:

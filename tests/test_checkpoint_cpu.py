@@ -144,3 +144,15 @@ def test_tokenizer_config_defaults_match_reference():
     c1, e1, _ = checkpoint.tokenizer_configs_from_dict(ref.to_dict())
     c2, e2, _ = checkpoint.tokenizer_configs_from_dict(tok)
     assert dataclasses.asdict(c1) == dataclasses.asdict(c2) and dataclasses.asdict(e1) == dataclasses.asdict(e2)
+
+
+def test_base_checkpoint_carries_speaker_encoder(tmp_path):
+    from qwen3_tts_b200 import checkpoint, synthetic
+    write_tiny_checkpoint(str(tmp_path), model_type="base")
+    tcfg, W, meta, _ = checkpoint.load_tts_checkpoint(str(tmp_path), device="cpu")
+    scfg = synthetic.cfg_speaker_encoder_tiny()
+    assert meta["tts_model_type"] == "base" and dataclasses.asdict(meta["speaker_encoder_config"]) == dataclasses.asdict(scfg)
+    want = synthetic.random_speaker_encoder_weights(scfg, seed=3)
+    got = meta["speaker_encoder_weights"]
+    assert set(got) == set(want) and all(got[k].dtype == torch.float32 and got[k].shape == want[k].shape for k in got)
+    assert not any(k.startswith("speaker_encoder.") for k in W)

@@ -97,3 +97,59 @@ def test_tokenizer_audio_input_normalisation():
     with pytest.raises(TypeError):
         T._normalize_audio_inputs([a, "x.wav"], 24000)
     assert T._is_url("https://example.com/a.wav") and not T._is_url("/tmp/a.wav")
+
+
+def test_create_voice_clone_prompt_host_logic():
+    """inference/qwen3_tts_model.py:355-458 with fake engines: broadcasting, ICL vs x-vector-only items, resampling to
+    the speaker encoder's rate, single batched encode when all sampling rates agree, error behaviour."""
+    from types import SimpleNamespace
+
+    class _Tok(_FakeTok):
+        def __init__(self):
+            self.calls = []
+
+        def encode(self, audios, sr=None, return_dict=True):
+            lst = audios if isinstance(audios, list) else [audios]
+            self.calls.append((len(lst), sr))
+            return SimpleNamespace(audio_codes=[torch.full((-(-len(a) * 24000 // sr // 1920), 16), i, dtype=torch.long)
+                                                for i, a in enumerate(lst)])
+
+    core = _FakeCore()
+    core.speech_tokenizer = _Tok()
+    core.speaker_encoder_sample_rate = 24000
+    core.tts_model_size = "1b7"
+    seen = []
+
+    def extract(audio, sr):
+        seen.append((audio.shape[0], sr, audio.dtype))
+        return torch.full((8,), float(audio.shape[0]))
+
+    core.extract_speaker_embedding = extract
+    m = Qwen3TTSModel(core, _proc)
+    a = np.zeros(24000, np.float32)
+    with pytest.raises(ValueError):                       # custom_voice models cannot build clone prompts (:400-406)
+        m.create_voice_clone_prompt((a, 24000), "hi")
+    core.tts_model_type = "base"
+    items = m.create_voice_clone_prompt([(a, 24000), (np.zeros((12000, 2), np.float32), 24000)], ref_text=["one", None],
+                                        x_vector_only_mode=[False, True])
+    assert core.speech_tokenizer.calls == [(2, 24000)]   # same sr -> one batched encode (:423-425)
+    assert [it.icl_mode for it in items] == [True, False] and [it.x_vector_only_mode for it in items] == [False, True]
+    assert items[0].ref_code.shape == (13, 16) and items[1].ref_code is None and items[0].ref_text == "one"
+    assert seen == [(24000, 24000, np.float32), (12000, 24000, np.float32)]   # stereo was mixed down
+    # different sampling rates -> per-item encode, x-vector input resampled to 24 kHz (:426-445)
+    seen.clear()
+    core.speech_tokenizer.calls.clear()
+    items = m.create_voice_clone_prompt([(a, 24000), (np.zeros(16000, np.float32), 16000)], ref_text="same text")
+    assert core.speech_tokenizer.calls == [(1, 24000), (1, 16000)] and [s[0] for s in seen] == [24000, 24000]
+    assert all(it.ref_text == "same text" and it.icl_mode for it in items)
+    with pytest.raises(ValueError):                       # ICL needs a transcript
+        m.create_voice_clone_prompt((a, 24000))
+    with pytest.raises(ValueError):                       # batch mismatch
+        m.create_voice_clone_prompt([(a, 24000), (a, 24000)], ref_text=["x"], x_vector_only_mode=[True, True])
+    with pytest.raises(ValueError):                       # bare ndarray needs its sampling rate
+        m.create_voice_clone_prompt(a, "hi")
+    with pytest.raises(TypeError):
+        m.create_voice_clone_prompt(123, "hi")
+    # and the items feed generate_voice_clone unchanged
+    wavs, fs = m.generate_voice_clone("t", language="english", ref_audio=(a, 24000), ref_text="r")
+    assert fs == 24000 and len(wavs) == 1
