@@ -1,0 +1,236 @@
+// Attention phase: per-head q/k RMSNorm + RoPE, KV append, single-query GQA with cross-CTA split-K combine.
+// Part of the ar_engine.cu translation unit (include order: ar_program, ar_gemv, ar_attention, ar_sampler,
+// the persistent kernel in ar_engine.cu, ar_prefill).
+#pragma once
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// attention phase (per (sequence, kv head, split) unit): q/k RMSNorm + RoPE, KV append, single-query GQA
+// ------------------------------------------------------------------------------------------------
+// one warp normalises + rotates one 128-vector; lane owns dims {l, l+32, l+64, l+96}
+__device__ __noinline__ void norm_rope_vec(const bf16* src, const bf16* nw, float eps, const bf16* cosr, const bf16* sinr,
+                                           float* out_f32, bf16* out_bf16) {
+  const int lane = threadIdx.x & 31;
+  float x[4], w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = bf2f(ldcg_bf16(src + lane + 32 * i));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w[i] = bf2f(nw[lane + 32 * i]);
+  // rotate_half pairs: (l, l+64) and (l+32, l+96); cos/sin tables are [64] (emb = cat(freqs, freqs))
+  const float c0 = bf2f(cosr[lane]), s0 = bf2f(sinr[lane]);
+  const float c1 = bf2f(cosr[lane + 32]), s1 = bf2f(sinr[lane + 32]);
+  float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+  ss = warp_sum(ss);
+  const float inv = rsqrtf(ss / (float)HD + eps);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = rbf(rbf(x[i] * inv) * w[i]);
+  float o[4];
+  o[0] = rbf(rbf(x[0] * c0) + rbf(-x[2] * s0));
+  o[2] = rbf(rbf(x[2] * c0) + rbf(x[0] * s0));
+  o[1] = rbf(rbf(x[1] * c1) + rbf(-x[3] * s1));
+  o[3] = rbf(rbf(x[3] * c1) + rbf(x[1] * s1));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (out_f32) out_f32[lane + 32 * i] = o[i];
+    else out_bf16[lane + 32 * i] = f2bf(o[i]);
+  }
+}
+
+__device__ __noinline__ void attn_phase(const Phase& ph, const KParams& P, unsigned char* smem, int frame) {
+  const StackDev& S = ph.stack == 0 ? P.talker : P.cp;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nh = S.nh, nkv = S.nkv, layers = S.layers, cap = S.cap;
+  const int R = nh / nkv;  // <= RMAX
+  const int B = P.B;
+  const int qkv_ld = (nh + 2 * nkv) * HD;
+  const int seqmode = ph.seqmode, layer = ph.layer;
+  const int nseq = B;
+  const float eps = S.eps;
+  const bf16 *qn = ph.qn, *kn = ph.kn;
+
+  int nsplit = 1;
+  if (seqmode == SEQ_DECODE) {
+    int cmax = 0;
+    for (int b = 0; b < B; ++b) cmax = max(cmax, P.len0[b]);
+    cmax += frame + 1;
+    const int byctx = (cmax + 127) >> 7;
+    const int bygrid = (int)gridDim.x / (B * nkv);
+    nsplit = max(1, min(min(byctx, bygrid), MAXSPLIT));
+  }
+  const int units = nseq * nkv * nsplit;
+
+  float* qs = reinterpret_cast<float*>(smem);                 // [nq<=2][RMAX][128]
+  float* red = qs + 2 * RMAX * HD;                            // [32 halfwarps][RMAX][130]
+  __shared__ int s_ticket;
+
+#pragma unroll 1
+  for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const int sp = unit % nsplit;
+    const int kvh = (unit / nsplit) % nkv;
+    const int si = unit / (nsplit * nkv);
+    int seq, q0, nq, qstride, ctx_end;
+    if (seqmode == SEQ_CP) { seq = si; q0 = si; nq = ph.nq; qstride = B; ctx_end = ph.ctx_end; }
+    else { seq = si; q0 = si; nq = 1; qstride = 0; ctx_end = P.len0[si] + frame + 1; }
+    const int SL = (ctx_end + nsplit - 1) / nsplit;
+    const int s0 = sp * SL, s1 = min(ctx_end, s0 + SL);
+    bf16* kc = S.kc + (((size_t)seq * layers + layer) * nkv + kvh) * (size_t)cap * HD;
+    bf16* vc = S.vc + (((size_t)seq * layers + layer) * nkv + kvh) * (size_t)cap * HD;
+
+    // ---- per query token: q heads -> smem (fp32), k (norm+rope) and v -> cache (owner split only)
+    const int nvec = nq * (R + 2);
+#pragma unroll 1
+    for (int v = warp; v < nvec; v += NWARPS) {
+      const int j = v / (R + 2), which = v - j * (R + 2);
+      const int col = q0 + j * qstride;
+      const int pos = ctx_end - nq + j;
+      const bool owner = (pos >= s0 && pos < s1);
+      const bf16* base = S.qkv + (size_t)col * qkv_ld;
+      const bf16* cosr = S.rope_cos + (size_t)pos * 64;
+      const bf16* sinr = S.rope_sin + (size_t)pos * 64;
+      if (which < R) {
+        norm_rope_vec(base + (kvh * R + which) * HD, qn, eps, cosr, sinr, qs + (j * RMAX + which) * HD, nullptr);
+      } else if (owner) {
+        if (which == R) {
+          norm_rope_vec(base + (nh + kvh) * HD, kn, eps, cosr, sinr, nullptr, kc + (size_t)pos * HD);
+        } else {
+          const bf16* vsrc = base + (nh + nkv + kvh) * HD;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) vc[(size_t)pos * HD + lane + 32 * i] = ldcg_bf16(vsrc + lane + 32 * i);
+        }
+      }
+    }
+    __threadfence_block();
+    __syncthreads();
+    PROF_MARK(2);
+
+    const float scale = rsqrtf((float)HD);
+    const int hw = warp * 2 + (lane >> 4), l16 = lane & 15;
+    const int rr_ = tid >> 7, dd = tid & (HD - 1);
+#pragma unroll 1
+    for (int j = 0; j < nq; ++j) {
+      const int col = q0 + j * qstride;
+      const int pos = ctx_end - nq + j;
+      const int e1 = min(s1, pos + 1);
+      float q[RMAX][8];
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[r][i] = (r < R) ? qs[(j * RMAX + r) * HD + l16 * 8 + i] : 0.f;
+      float m[RMAX], l[RMAX], o[RMAX][8];
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) {
+        m[r] = -INFINITY; l[r] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[r][i] = 0.f;
+      }
+      // warp-uniform trip count (full-mask shuffles below); each half-warp handles 2 tokens per iteration so
+      // that 4 independent 16-byte loads are in flight before the dependent softmax update
+#pragma unroll 1
+      for (int tb = s0 + warp * 4; tb < e1; tb += NWARPS * 4) {
+        const int tk0 = tb + (lane >> 4), tk1 = tk0 + 2;
+        uint4 kv[2], vv[2];
+        kv[0] = kv[1] = vv[0] = vv[1] = make_uint4(0, 0, 0, 0);
+        if (tk0 < e1) { kv[0] = ldcg16(kc + (size_t)tk0 * HD + l16 * 8); vv[0] = ldcg16(vc + (size_t)tk0 * HD + l16 * 8); }
+        if (tk1 < e1) { kv[1] = ldcg16(kc + (size_t)tk1 * HD + l16 * 8); vv[1] = ldcg16(vc + (size_t)tk1 * HD + l16 * 8); }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {  // fully unrolled: register arrays must keep compile-time indices (no local memory)
+          const bool valid = (u == 0 ? tk0 : tk1) < e1;
+          const uint4 kk = kv[u], v4 = vv[u];
+          const float kf[8] = {bf16lo(kk.x), bf16hi(kk.x), bf16lo(kk.y), bf16hi(kk.y),
+                               bf16lo(kk.z), bf16hi(kk.z), bf16lo(kk.w), bf16hi(kk.w)};
+          const float vf[8] = {bf16lo(v4.x), bf16hi(v4.x), bf16lo(v4.y), bf16hi(v4.y),
+                               bf16lo(v4.z), bf16hi(v4.z), bf16lo(v4.w), bf16hi(v4.w)};
+#pragma unroll
+          for (int r = 0; r < RMAX; ++r) {
+            if (r < R) {
+              float d = 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) d += q[r][i] * kf[i];
+              d += __shfl_xor_sync(0xffffffffu, d, 8);
+              d += __shfl_xor_sync(0xffffffffu, d, 4);
+              d += __shfl_xor_sync(0xffffffffu, d, 2);
+              d += __shfl_xor_sync(0xffffffffu, d, 1);
+              if (valid) {
+                d *= scale;
+                const float mn = fmaxf(m[r], d);
+                const float corr = __expf(m[r] - mn);  // exp(-inf)=0 on the first token
+                const float p = __expf(d - mn);
+                l[r] = l[r] * corr + p;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[r][i] = o[r][i] * corr + p * vf[i];
+                m[r] = mn;
+              }
+            }
+          }
+        }
+      }
+      // ---- combine the 32 half-warps
+      PROF_MARK(3);
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < RMAX; ++r) {
+        if (r < R) {
+          float* rr = red + ((size_t)hw * RMAX + r) * 130;
+          if (l16 == 0) { rr[0] = m[r]; rr[1] = l[r]; }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rr[2 + l16 * 8 + i] = o[r][i];
+        }
+      }
+      __syncthreads();
+      float M = -INFINITY, L = 0.f, O = 0.f;
+      // token t of this split maps to half-warp ((t>>2)<<1) | (t&1): only the first nhw half-warps hold data
+      const int ntok = max(e1 - s0, 0);
+      const int nhw = min(2 * NWARPS, ((ntok + 3) >> 2) << 1);
+      if (rr_ < R) {
+#pragma unroll 2
+        for (int h2 = 0; h2 < nhw; ++h2) M = fmaxf(M, red[((size_t)h2 * RMAX + rr_) * 130]);
+#pragma unroll 2
+        for (int h2 = 0; h2 < nhw; ++h2) {
+          const float* rp = red + ((size_t)h2 * RMAX + rr_) * 130;
+          const float wgt = (rp[0] == -INFINITY) ? 0.f : __expf(rp[0] - M);
+          L += rp[1] * wgt;
+          O += rp[2 + dd] * wgt;
+        }
+      }
+      PROF_MARK(4);
+      bf16* outp = S.attn + (size_t)col * (nh * HD) + (kvh * R + rr_) * HD + dd;
+      if (nsplit == 1) {
+        if (rr_ < R) *outp = f2bf(O / L);
+      } else {
+        // cross-CTA split combine: publish (M,L,O) and let the last arriver finish (deterministic order)
+        float* sb0 = P.split_buf + (((size_t)(seq * nkv + kvh) * MAXSPLIT) * RMAX) * 130;
+        float* sb = sb0 + ((size_t)sp * RMAX) * 130;
+        if (rr_ < R) {
+          if (dd == 0) { sb[rr_ * 130] = M; sb[rr_ * 130 + 1] = L; }
+          sb[rr_ * 130 + 2 + dd] = O;
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_ticket = (int)atomicAdd(&P.st->split_cnt[seq * nkv + kvh], 1u);
+        __syncthreads();
+        if (s_ticket == nsplit - 1) {
+          __threadfence();
+          if (rr_ < R) {
+            float M2 = -INFINITY, L2 = 0.f, O2 = 0.f;
+#pragma unroll 1
+            for (int s2 = 0; s2 < nsplit; ++s2) M2 = fmaxf(M2, ldcgf(sb0 + ((size_t)s2 * RMAX + rr_) * 130));
+#pragma unroll 1
+            for (int s2 = 0; s2 < nsplit; ++s2) {
+              const float* rp = sb0 + ((size_t)s2 * RMAX + rr_) * 130;
+              const float mm = ldcgf(rp);
+              const float wgt = (mm == -INFINITY) ? 0.f : __expf(mm - M2);
+              L2 += ldcgf(rp + 1) * wgt;
+              O2 += ldcgf(rp + 2 + dd) * wgt;
+            }
+            *outp = f2bf(O2 / L2);
+          }
+          if (tid == 0) P.st->split_cnt[seq * nkv + kvh] = 0;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace
