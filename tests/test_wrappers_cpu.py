@@ -153,3 +153,15 @@ def test_create_voice_clone_prompt_host_logic():
     # and the items feed generate_voice_clone unchanged
     wavs, fs = m.generate_voice_clone("t", language="english", ref_audio=(a, 24000), ref_text="r")
     assert fs == 24000 and len(wavs) == 1
+
+
+def test_public_names_match_the_reference_package():
+    """qwen_tts/__init__.py:21-22 exports exactly these three names."""
+    from qwen3_tts_b200 import Qwen3TTSModel as A, Qwen3TTSTokenizer as B, VoiceClonePromptItem as C
+    from qwen3_tts_b200 import model
+    assert A is model.Qwen3TTSModel and B is model.Qwen3TTSTokenizer and C is model.VoiceClonePromptItem
+    assert all(hasattr(A, n) for n in ("from_pretrained", "generate_custom_voice", "generate_voice_design",
+                                       "generate_voice_clone", "create_voice_clone_prompt", "get_supported_speakers",
+                                       "get_supported_languages"))
+    assert all(hasattr(B, n) for n in ("from_pretrained", "encode", "decode", "get_model_type", "get_input_sample_rate",
+                                       "get_output_sample_rate", "get_encode_downsample_rate", "get_decode_upsample_rate"))
