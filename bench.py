@@ -66,6 +66,11 @@ def parse():
     return ap.parse_args()
 
 
+def _pin(t):
+    """Pinned host memory for the GPU arm's H2D copies; the CPU reference arm also runs where no driver exists."""
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
 def workload(args, H):
     """Synthetic inputs of config[2]'s shape: seeded, bf16, pinned host memory."""
     B = args.batch
@@ -76,10 +81,10 @@ def workload(args, H):
     embs, trail = [], []
     for i, L in enumerate(lens):
         g = torch.Generator().manual_seed(1000 + i)
-        embs.append((torch.randn(L, H, generator=g) * 0.5).to(torch.bfloat16).pin_memory())
+        embs.append(_pin((torch.randn(L, H, generator=g) * 0.5).to(torch.bfloat16)))
         trail.append(torch.zeros(0, H, dtype=torch.bfloat16))
     g = torch.Generator().manual_seed(999)
-    pad = (torch.randn(H, generator=g) * 0.1).to(torch.bfloat16).pin_memory()
+    pad = _pin((torch.randn(H, generator=g) * 0.1).to(torch.bfloat16))
     return lens, embs, trail, pad
 
 
@@ -226,7 +231,7 @@ def main():
     from qwen3_tts_b200 import synthetic
     cfg = model_cfg(args.model)
     ccfg = q.CodecConfig() if args.model != "tiny" else q.CodecConfig(
-        codebook_size=64, codebook_dim=64, hidden_size=64, latent_dim=64, num_heads=4, num_kv_heads=4, head_dim=16,
+        codebook_size=2048, codebook_dim=64, hidden_size=64, latent_dim=64, num_heads=4, num_kv_heads=4, head_dim=16,
         sliding_window=6, intermediate_size=96, num_layers=2, decoder_dim=256)
     H = cfg.talker.hidden_size
     lens, embs, trail, pad = workload(args, H)
