@@ -298,3 +298,123 @@ def random_weights(cfg: CodecCfg, seed=0, dtype=torch.float32):
     conv(f"decoder.{n + 2}.conv", 1, cl, 7)
     W[f"decoder.{n + 2}.conv.weight"] *= 0.3
     return W
+
+
+# ----------------------------------------------------------------------------------------------
+# Stateful streaming decoder (a NEW surface — the reference only has chunked_decode, which is not
+# equal to the full forward after the first chunk, F9).  Every layer of the decoder is causal, so a packet can be
+# decoded exactly given a bounded amount of per-layer history: this class states WHICH history (the spec the CUDA
+# engine's stateful path has to implement) and tests/test_oracle_golden.py proves packets == decoder_forward(full).
+#   conv k (stride 1, dilation d)      : the last (k-1)*d input samples          (zeros before the first packet = causal pad)
+#   ConvTranspose k=2r, stride r       : the last input sample (overlap-add of two half kernels)
+#   ConvTranspose k=stride             : nothing
+#   sliding-window transformer         : K/V of the last window-1 frames per layer + the absolute position (RoPE)
+# ----------------------------------------------------------------------------------------------
+class StreamingDecoder:
+    def __init__(self, W, cfg: CodecCfg, batch: int = 1):
+        self.W, self.cfg, self.B = W, cfg, batch
+        self.state = {}
+        self.pos = 0  # frames consumed so far
+
+    def _conv(self, name, x, w, b, dilation=1, groups=1):
+        ctx = (w.shape[-1] - 1) * dilation
+        prev = self.state.get(name)
+        if prev is None:
+            prev = torch.zeros(x.shape[0], x.shape[1], ctx, dtype=x.dtype)
+        xx = torch.cat([prev, x], dim=-1)
+        if ctx:
+            self.state[name] = xx[..., xx.shape[-1] - ctx:]
+        return F.conv1d(xx, w, b, dilation=dilation, groups=groups)
+
+    def _convT(self, name, x, w, b, stride):
+        k = w.shape[-1]
+        if k == stride:                      # no overlap between output blocks
+            return F.conv_transpose1d(x, w, b, stride=stride)
+        assert k == 2 * stride, "decoder blocks use k = 2*stride (…v2.py:638-658)"
+        prev = self.state.get(name)
+        if prev is None:
+            prev = torch.zeros(x.shape[0], x.shape[1], 1, dtype=x.dtype)
+        xx = torch.cat([prev, x], dim=-1)
+        self.state[name] = x[..., -1:]
+        y = F.conv_transpose1d(xx, w, b, stride=stride)
+        return y[..., stride: stride + x.shape[-1] * stride]
+
+    def _transformer(self, x):
+        W, cfg = self.W, self.cfg
+        B, T, _ = x.shape
+        p = "pre_transformer"
+        x = F.linear(x, W[f"{p}.input_proj.weight"], W[f"{p}.input_proj.bias"])
+        pos = (self.pos + torch.arange(T))[None].expand(B, -1)
+        cos, sin = rope_cos_sin(pos, cfg.head_dim, cfg.rope_theta, x.dtype)
+        nrep = cfg.num_heads // cfg.num_kv_heads
+        for i in range(cfg.num_layers):
+            lp = f"{p}.layers.{i}"
+            res = x
+            h = rms_norm(x, W[f"{lp}.input_layernorm.weight"], cfg.rms_eps)
+            q = F.linear(h, W[f"{lp}.self_attn.q_proj.weight"]).view(B, T, -1, cfg.head_dim).transpose(1, 2)
+            k = F.linear(h, W[f"{lp}.self_attn.k_proj.weight"]).view(B, T, -1, cfg.head_dim).transpose(1, 2)
+            v = F.linear(h, W[f"{lp}.self_attn.v_proj.weight"]).view(B, T, -1, cfg.head_dim).transpose(1, 2)
+            q, k = apply_rope(q, k, cos, sin)
+            pk, pv = self.state.get(f"k{i}"), self.state.get(f"v{i}")
+            if pk is not None:
+                k, v = torch.cat([pk, k], 2), torch.cat([pv, v], 2)
+            keep = cfg.sliding_window - 1
+            self.state[f"k{i}"], self.state[f"v{i}"] = k[:, :, -keep:] if keep else k[:, :, :0], v[:, :, -keep:] if keep else v[:, :, :0]
+            S = k.shape[2]
+            kpos = self.pos + T - S + torch.arange(S)          # absolute positions of the cached + new keys
+            qpos = self.pos + torch.arange(T)
+            allowed = (kpos[None, :] <= qpos[:, None]) & (qpos[:, None] - kpos[None, :] < cfg.sliding_window)
+            mask = torch.zeros(T, S, dtype=x.dtype).masked_fill(~allowed, torch.finfo(x.dtype).min)[None, None]
+            kk, vv = (k.repeat_interleave(nrep, dim=1), v.repeat_interleave(nrep, dim=1)) if nrep > 1 else (k, v)
+            w = torch.matmul(q, kk.transpose(2, 3)) * (cfg.head_dim ** -0.5) + mask
+            w = F.softmax(w, dim=-1, dtype=torch.float32).to(q.dtype)
+            a = torch.matmul(w, vv).transpose(1, 2).reshape(B, T, -1)
+            a = F.linear(a, W[f"{lp}.self_attn.o_proj.weight"])
+            x = res + W[f"{lp}.self_attn_layer_scale.scale"] * a
+            res = x
+            h = rms_norm(x, W[f"{lp}.post_attention_layernorm.weight"], cfg.rms_eps)
+            h = F.linear(F.silu(F.linear(h, W[f"{lp}.mlp.gate_proj.weight"])) * F.linear(h, W[f"{lp}.mlp.up_proj.weight"]),
+                         W[f"{lp}.mlp.down_proj.weight"])
+            x = res + W[f"{lp}.mlp_layer_scale.scale"] * h
+        x = rms_norm(x, W[f"{p}.norm.weight"], cfg.rms_eps)
+        return F.linear(x, W[f"{p}.output_proj.weight"], W[f"{p}.output_proj.bias"])
+
+    @torch.no_grad()
+    def push(self, codes):
+        """codes: (B, K, n) the next n frames -> wav (B, 1, n * total_upsample), equal to the same slice of
+        decoder_forward over everything pushed so far."""
+        W, cfg = self.W, self.cfg
+        h = rvq_decode(W, cfg, codes)
+        h = self._conv("pre_conv", h, W["pre_conv.conv.weight"], W["pre_conv.conv.bias"]).transpose(1, 2)
+        h = self._transformer(h).permute(0, 2, 1)
+        for i, f in enumerate(cfg.upsampling_ratios):
+            h = self._convT(f"up{i}", h, W[f"upsample.{i}.0.conv.weight"], W[f"upsample.{i}.0.conv.bias"], f)
+            q = f"upsample.{i}.1"
+            C = h.shape[1]
+            inp = h
+            g = self._conv(f"dw{i}", h, W[f"{q}.dwconv.conv.weight"], W[f"{q}.dwconv.conv.bias"], groups=C).permute(0, 2, 1)
+            g = F.layer_norm(g, (C,), W[f"{q}.norm.weight"], W[f"{q}.norm.bias"], eps=1e-6)
+            g = F.linear(F.gelu(F.linear(g, W[f"{q}.pwconv1.weight"], W[f"{q}.pwconv1.bias"])), W[f"{q}.pwconv2.weight"],
+                         W[f"{q}.pwconv2.bias"])
+            h = inp + (W[f"{q}.gamma"] * g).permute(0, 2, 1)
+        w = self._conv("dec0", h, W["decoder.0.conv.weight"], W["decoder.0.conv.bias"])
+        for i, r in enumerate(cfg.upsample_rates):
+            p = f"decoder.{i + 1}.block"
+            w = snake_beta(w, W[f"{p}.0.alpha"], W[f"{p}.0.beta"])
+            w = self._convT(f"ct{i}", w, W[f"{p}.1.conv.weight"], W[f"{p}.1.conv.bias"], r)
+            for u, dil in enumerate((1, 3, 9)):
+                q = f"{p}.{u + 2}"
+                res = w
+                w = snake_beta(w, W[f"{q}.act1.alpha"], W[f"{q}.act1.beta"])
+                w = self._conv(f"c1_{i}_{u}", w, W[f"{q}.conv1.conv.weight"], W[f"{q}.conv1.conv.bias"], dilation=dil)
+                w = snake_beta(w, W[f"{q}.act2.alpha"], W[f"{q}.act2.beta"])
+                w = F.conv1d(w, W[f"{q}.conv2.conv.weight"], W[f"{q}.conv2.conv.bias"]) + res
+        n = len(cfg.upsample_rates)
+        w = snake_beta(w, W[f"decoder.{n + 1}.alpha"], W[f"decoder.{n + 1}.beta"])
+        w = self._conv("out", w, W[f"decoder.{n + 2}.conv.weight"], W[f"decoder.{n + 2}.conv.bias"])
+        self.pos += codes.shape[-1]
+        return w.clamp(min=-1, max=1)
+
+    def state_bytes(self, dtype_bytes=2):
+        """History the engine has to carry per row (bf16 by default)."""
+        return sum(int(v.numel()) // max(self.B, 1) * dtype_bytes for v in self.state.values())

@@ -63,3 +63,24 @@ def test_speaker_encoder_against_golden():
     emb = OS.speaker_encoder(W, cfg, torch.from_numpy(z["mel"]).transpose(1, 2))
     assert np.abs(emb.numpy() - z["emb"]).max() < 1e-5
     assert np.abs(OS.extract_speaker_embedding(W, cfg, wav[0]).numpy() - z["emb"][0]).max() < 1e-4
+
+
+def test_streaming_decoder_spec_equals_full_forward():
+    """oracle/codec.py::StreamingDecoder (the per-layer history a stateful codec decoder must carry, SURVEY §8f-2):
+    ragged packets concatenated == one causal forward over all frames, incl. the sliding-window KV trim (window 6 < 23
+    frames) and a batch of two rows."""
+    cfg = OC.cfg_tiny_codec()
+    W = OC.random_weights(cfg, seed=4)
+    g = torch.Generator().manual_seed(0)
+    codes = torch.randint(0, cfg.codebook_size, (2, 16, 23), generator=g)
+    full = OC.decoder_forward(W, cfg, codes)
+    sd = OC.StreamingDecoder(W, cfg, batch=2)
+    outs, s = [], 0
+    for n in (4, 4, 1, 7, 2, 5):
+        outs.append(sd.push(codes[..., s:s + n]))
+        s += n
+    out = torch.cat(outs, -1)
+    assert out.shape == full.shape and (out - full).abs().max() < 2e-5
+    # unlike the reference's chunked_decode, which drifts from the full forward after its first chunk (SURVEY F9)
+    ch = OC.chunked_decode(W, cfg, codes, chunk_size=8, left_context_size=2)
+    assert (ch - full).abs().max() > 1e-3
