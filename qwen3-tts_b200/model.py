@@ -299,9 +299,9 @@ class Qwen3TTSTokenizer:
         return resample_poly(a.astype(np.float32), int(target_sr) // g, int(sr) // g).astype(np.float32)
 
     @classmethod
-    def load_audio(cls, x: str, target_sr: int) -> np.ndarray:
-        """:121-157 — wav path, URL or base64 (raw / data URL) -> mono float32 at target_sr.  PCM/float WAV only here
-        (scipy.io.wavfile; the reference's soundfile/librosa also read flac/ogg/mp3)."""
+    def _load_audio_to_np(cls, x: str) -> Tuple[np.ndarray, int]:
+        """wav path, URL or base64 (raw / data URL) -> (mono float32 waveform, its sampling rate).  PCM / float WAV only
+        (scipy.io.wavfile; the reference's soundfile / librosa also read flac, ogg, mp3)."""
         import base64
         import io
         from scipy.io import wavfile
@@ -322,7 +322,13 @@ class Qwen3TTSTokenizer:
             audio = (audio.astype(np.float32) - 128.0) / 128.0
         audio = audio.astype(np.float32)
         if audio.ndim > 1:
-            audio = np.mean(audio, axis=-1)
+            audio = np.mean(audio, axis=-1).astype(np.float32)
+        return audio, int(sr)
+
+    @classmethod
+    def load_audio(cls, x: str, target_sr: int) -> np.ndarray:
+        """:121-157 — wav path, URL or base64 -> mono float32 at target_sr."""
+        audio, sr = cls._load_audio_to_np(x)
         return cls._resample(audio, sr, target_sr)
 
     @classmethod
@@ -559,24 +565,7 @@ class Qwen3TTSModel:
         out: List[Tuple[np.ndarray, int]] = []
         for a in items:
             if isinstance(a, str):
-                from scipy.io import wavfile
-                import base64
-                import io
-                if Qwen3TTSTokenizer._is_url(a):
-                    import urllib.request
-                    with urllib.request.urlopen(a) as resp:
-                        src = io.BytesIO(resp.read())
-                elif Qwen3TTSTokenizer._is_probably_base64(a):
-                    b64 = a.split(",", 1)[1] if ("," in a and a.strip().startswith("data:")) else a
-                    src = io.BytesIO(base64.b64decode(b64))
-                else:
-                    src = a
-                sr, audio = wavfile.read(src)
-                if audio.dtype.kind == "i":
-                    audio = audio.astype(np.float32) / float(np.iinfo(audio.dtype).max + 1)
-                elif audio.dtype.kind == "u":
-                    audio = (audio.astype(np.float32) - 128.0) / 128.0
-                out.append((audio.astype(np.float32), int(sr)))
+                out.append(Qwen3TTSTokenizer._load_audio_to_np(a))
             elif isinstance(a, tuple) and len(a) == 2 and isinstance(a[0], np.ndarray):
                 out.append((a[0].astype(np.float32), int(a[1])))
             elif isinstance(a, np.ndarray):
