@@ -198,8 +198,7 @@ int q3_codec_enc_debug_capture(q3_codec_enc* e, int32_t stage, float* dst_dev, i
 
 /* ---------------------------------------------------------------- speaker x-vector (voice cloning)
  * Replaces Qwen3TTSForConditionalGeneration.extract_speaker_embedding (core/models/modeling_qwen3_tts.py:1941-1954):
- * mel_spectrogram (:396-448) + Qwen3TTSSpeakerEncoder.forward (:371-393).  fp32.  NOT YET RUN ON HARDWARE (written
- * after round 1's GPU budget was spent; see csrc/speaker_encoder.cu). */
+ * mel_spectrogram (:396-448) + Qwen3TTSSpeakerEncoder.forward (:371-393).  fp32. */
 typedef struct {
   int32_t mel_dim, enc_dim;                 /* Qwen3TTSSpeakerEncoderConfig (configuration_qwen3_tts.py:47-57) */
   int32_t n_blocks;                         /* len(enc_channels) */

@@ -3,9 +3,8 @@
 // mel_spectrogram (:396-448) + Qwen3TTSSpeakerEncoder.forward (:371-393) with TimeDelayNetBlock :229-250, Res2NetBlock
 // :95-126, SqueezeExcitationBlock :129-157, SqueezeExcitationRes2NetBlock :253-297, AttentiveStatisticsPooling :160-226.
 //
-// STATUS: written at the end of round 1 after the round's GPU budget was spent — compiled for sm_100a, NOT yet executed
-// on hardware.  Its GPU tests (tests/test_gpu_speaker_encoder.py) are marked xfail(strict=False) until a B200 run
-// confirms them; nothing in bench.py / smoke() / the other tests touches this file.
+// Validated on a B200 against the CPU oracle (tests/test_gpu_speaker_encoder.py: log-mel, ECAPA embedding and the
+// waveform-to-embedding path at tiny and default shapes, golden vectors).
 //
 // fp32 throughout, activations [B][C][T] (time contiguous).  One generalised direct-convolution kernel serves every
 // Conv1d: reflect "same" padding with dilation, channel-sliced input/output (Res2Net chunks and the multi-layer feature

@@ -1,9 +1,6 @@
 """Host side of the speaker x-vector path (Qwen3TTSForConditionalGeneration.extract_speaker_embedding,
 core/models/modeling_qwen3_tts.py:1941-1954) on libqwen3tts_b200.so.
 
-STATUS: written after round 1's GPU budget was spent; the CUDA side (csrc/speaker_encoder.cu) has not run on hardware
-yet — see tests/test_gpu_speaker_encoder.py.
-
 `weights`: the reference's `speaker_encoder.*` state_dict entries with the prefix stripped, any float dtype.  The mel
 front-end tables are computed here on the CPU: Hann window (torch.hann_window, periodic), the exact DFT twiddles, and the
 Slaney-scale, area-normalised triangular filterbank that `librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax)` produces

