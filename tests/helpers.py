@@ -90,7 +90,7 @@ def tiny_checkpoint_configs():
     return top, tok, gen
 
 
-def write_tiny_checkpoint(directory, device="cpu", sharded=False, seed=0, model_type="custom_voice"):
+def write_tiny_checkpoint(directory, device="cpu", sharded=False, seed=0, model_type="custom_voice", spk_enc_dim=24):
     """Write a complete synthetic checkpoint directory in the reference's on-disk format; returns what was written
     (tts weights, decoder weights, encoder weights) for comparison."""
     import json
@@ -104,7 +104,8 @@ def write_tiny_checkpoint(directory, device="cpu", sharded=False, seed=0, model_
     cfg = synthetic.cfg_tiny()
     W = {k: v.cpu().contiguous() for k, v in synthetic.random_tts_weights(cfg, device=device, seed=seed, with_text=True).items()}
     if model_type == "base":   # Base checkpoints carry the ECAPA speaker encoder (modeling_qwen3_tts.py:1822-1825)
-        scfg = synthetic.cfg_speaker_encoder_tiny()
+        import dataclasses as _dc
+        scfg = _dc.replace(synthetic.cfg_speaker_encoder_tiny(), enc_dim=spk_enc_dim)
         top = dict(top, tts_model_type="base",
                    speaker_encoder_config=dict(mel_dim=scfg.mel_dim, enc_dim=scfg.enc_dim, enc_channels=list(scfg.enc_channels),
                                                enc_kernel_sizes=list(scfg.enc_kernel_sizes), enc_dilations=list(scfg.enc_dilations),
