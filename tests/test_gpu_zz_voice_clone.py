@@ -1,10 +1,11 @@
-"""Voice cloning from raw audio, end to end on the GPU (BASELINE config 5 in miniature).  Kept in its own file, sorted
-after every other GPU test, because it has not run on hardware yet (see the xfail reason)."""
+"""Checkpoint loading and voice cloning from raw audio, end to end on the GPU (BASELINE config 5 in miniature).  Kept in
+their own file, sorted after every other GPU test, because these two tests were written after round 1's GPU budget was
+spent and have not run on hardware yet (see the xfail reason); every engine they drive is validated by the files before."""
 import numpy as np
 import pytest
 import torch
 
-from tests.test_gpu_e2e import DEV, _proc
+from tests.test_gpu_e2e import DEV, _build, _proc
 
 pytestmark = pytest.mark.gpu
 
@@ -34,3 +35,26 @@ def test_voice_clone_from_raw_audio_end_to_end(tmp_path):
     assert all(np.array_equal(a, b) for a, b in zip(wavs, again))
     one, _ = m.generate_voice_clone("hello there", language="english", ref_audio=ref, ref_text="reference words", **kw)
     assert np.array_equal(one[0], wavs[0])
+
+
+@pytest.mark.xfail(strict=False, reason="not yet run on a B200 (written after round 1's GPU budget was spent); the loader is "
+                                        "CPU-tested, the engines are hardware-validated")
+def test_from_pretrained_equals_direct_construction(tmp_path):
+    """A checkpoint directory in the reference's on-disk format (config.json, safetensors, speech_tokenizer/,
+    generation_config.json) loaded through Qwen3TTSModel.from_pretrained produces the same waveforms as the model
+    built directly from the same tensors; the loaded tokenizer also encodes."""
+    from tests.helpers import write_tiny_checkpoint
+    from qwen3_tts_b200.model import Qwen3TTSModel
+    write_tiny_checkpoint(str(tmp_path), device=DEV, seed=0)
+    m2 = Qwen3TTSModel.from_pretrained(str(tmp_path), device_map=DEV, processor=_proc, max_batch=8, max_ctx=256,
+                                       codec_max_frames=128)
+    cfg, core, m = _build()
+    kw = dict(max_new_tokens=9, do_sample=True, top_k=50, top_p=1.0, temperature=0.9, repetition_penalty=1.05,
+              subtalker_dosample=True, subtalker_top_k=50, subtalker_top_p=1.0, subtalker_temperature=0.9, seed=7)
+    args = (["hello there", "x"],)
+    a, _ = m.generate_custom_voice(*args, speaker=["alice", "bob"], language=["english", "auto"], **kw)
+    b, fs = m2.generate_custom_voice(*args, speaker=["alice", "bob"], language=["english", "auto"], **kw)
+    assert fs == 24000 and all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert m2.generate_defaults["top_k"] == 40 and m2.get_supported_speakers() == ["alice", "bob"]
+    codes = m2.model.speech_tokenizer.encode(np.zeros(6000, np.float32), sr=24000).audio_codes
+    assert tuple(codes[0].shape) == (4, 16) and codes[0].dtype == torch.long
