@@ -1,6 +1,5 @@
-"""Checkpoint loading and voice cloning from raw audio, end to end on the GPU (BASELINE config 5 in miniature).  Kept in
-their own file, sorted after every other GPU test, because these two tests were written after round 1's GPU budget was
-spent and have not run on hardware yet (see the xfail reason); every engine they drive is validated by the files before."""
+"""Checkpoint loading and voice cloning from raw audio, end to end on the GPU (BASELINE config 5 in miniature): both green
+on a B200 (last GPU call of round 1)."""
 import numpy as np
 import pytest
 import torch
@@ -10,8 +9,6 @@ from tests.test_gpu_e2e import DEV, _build, _proc
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.xfail(strict=False, reason="composition of hardware-validated parts (codec encoder, speaker encoder, AR engine, "
-                                        "codec decoder) written after round 1's GPU budget was spent; not itself run on a B200 yet")
 def test_voice_clone_from_raw_audio_end_to_end(tmp_path):
     """BASELINE config 5 in miniature: Base checkpoint -> create_voice_clone_prompt(raw 24 kHz audio + transcript)
     (codec encoder for ref_code, speaker encoder for the x-vector) -> generate_voice_clone (ICL prefill, AR decode, codec
@@ -37,8 +34,6 @@ def test_voice_clone_from_raw_audio_end_to_end(tmp_path):
     assert np.array_equal(one[0], wavs[0])
 
 
-@pytest.mark.xfail(strict=False, reason="not yet run on a B200 (written after round 1's GPU budget was spent); the loader is "
-                                        "CPU-tested, the engines are hardware-validated")
 def test_from_pretrained_equals_direct_construction(tmp_path):
     """A checkpoint directory in the reference's on-disk format (config.json, safetensors, speech_tokenizer/,
     generation_config.json) loaded through Qwen3TTSModel.from_pretrained produces the same waveforms as the model
