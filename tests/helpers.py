@@ -114,6 +114,7 @@ def write_tiny_checkpoint(directory, device="cpu", sharded=False, seed=0, model_
         for k, v in synthetic.random_speaker_encoder_weights(scfg, seed=seed + 3).items():
             W["speaker_encoder." + k] = v.to(torch.bfloat16).contiguous()
     else:
+        top = dict(top, tts_model_type=model_type)
         W["speaker_encoder.fc.weight"] = torch.zeros(4, 4, 1, dtype=torch.bfloat16)  # must be skipped by the loader
     json.dump(top, open(os.path.join(directory, "config.json"), "w"))
     json.dump(gen, open(os.path.join(directory, "generation_config.json"), "w"))

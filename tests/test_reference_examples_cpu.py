@@ -132,3 +132,12 @@ def test_custom_voice_and_voice_design_example_call_shapes(stubbed, tmp_path):
     with pytest.raises(ValueError):
         tts.generate_voice_design(text="x", instruct="y")           # wrong model type
     assert tts.get_supported_speakers() == ["alice", "bob"] and "english" in tts.get_supported_languages()
+    vd_dir = tmp_path / "vd"
+    write_tiny_checkpoint(str(vd_dir), model_type="voice_design")
+    vd = stubbed.Qwen3TTSModel.from_pretrained(str(vd_dir), device_map="cpu", processor=_proc)
+    w, sr = vd.generate_voice_design(text="hello there", language="English", instruct="a calm, low voice")
+    assert sr == 24000 and len(w) == 1
+    w, _ = vd.generate_voice_design(text=["a", "b"], language=["Chinese", "English"], instruct=["warm", "bright"])
+    assert len(w) == 2
+    with pytest.raises(ValueError):
+        vd.generate_custom_voice(text="x", speaker="alice")         # wrong model type the other way round
