@@ -84,3 +84,23 @@ def test_streaming_decoder_spec_equals_full_forward():
     # unlike the reference's chunked_decode, which drifts from the full forward after its first chunk
     ch = OC.chunked_decode(W, cfg, codes, chunk_size=8, left_context_size=2)
     assert (ch - full).abs().max() > 1e-3
+
+
+def test_oracle_rows_are_independent_and_padding_invariant():
+    """utterances never interact (batching is left-padding + masking, modeling_qwen3_tts.py:2239-2254).
+    Greedy codes of a row must not depend on what else is in the batch, nor on how far it is left-padded — the property
+    that makes the data-parallel split (and the engine's unpadded per-row prefill) exact."""
+    cfg = OT.cfg_tiny()
+    W = OT.random_weights(cfg, seed=2, with_text=False)
+    g = torch.Generator().manual_seed(3)
+    H = cfg.talker.hidden_size
+    embs = [torch.randn(n, H, generator=g) * 0.5 for n in (4, 11, 7)]
+    trail = [torch.randn(n, H, generator=g) * 0.1 for n in (0, 3, 1)]
+    pad = torch.randn(H, generator=g) * 0.1
+    sp = OT.SamplingCfg(do_sample=False, subtalker_dosample=False, max_new_tokens=6, suppress_eos=True)
+    full = OT.generate(W, cfg, embs, trail, pad, sp).codes
+    for i in range(3):
+        solo = OT.generate(W, cfg, [embs[i]], [trail[i]], pad, sp).codes[0]
+        assert torch.equal(solo, full[i]), i
+    rev = OT.generate(W, cfg, embs[::-1], trail[::-1], pad, sp).codes[::-1]
+    assert all(torch.equal(a, b) for a, b in zip(rev, full))
