@@ -220,6 +220,32 @@ def codec_encoder_probe(dev):
     return res
 
 
+def speaker_encoder_probe(dev):
+    """3 s of 24 kHz audio -> (1024,) x-vector (log-mel + ECAPA-TDNN, fp32, default shapes, seeded random weights)."""
+    import qwen3_tts_b200  # noqa: F401
+    from qwen3_tts_b200 import synthetic
+    from qwen3_tts_b200.config import SpeakerEncoderConfig
+    from qwen3_tts_b200.speaker_encoder import SpeakerEncoder
+    scfg = SpeakerEncoderConfig()
+    enc = SpeakerEncoder(scfg, synthetic.random_speaker_encoder_weights(scfg, seed=1), device=dev)
+    res = {"what": "speaker x-vector, 72000 samples (3 s) per row, fp32, ms per call", "launches": None}
+    for B in (1, 8):
+        wav = (torch.randn(B, 72000, device=dev) * 0.1).clamp(-1, 1)
+        for _ in range(2):
+            emb = enc.embed_waveform(wav)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            emb = enc.embed_waveform(wav)
+        e1.record()
+        torch.cuda.synchronize()
+        assert tuple(emb.shape) == (B, scfg.enc_dim) and bool(torch.isfinite(emb).all())
+        res[f"ms_batch{B}"] = e0.elapsed_time(e1) / 5
+    res["launches"] = enc.last_launches()
+    return res
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -416,10 +442,12 @@ def main():
                                          f"fp32, {ncores} threads, extrapolated to {N} frames", **det}
     # ---- side measurement, never part of `value`: the codec ENCODER (BASELINE config 1's encode half)
     if rank == 0 and world == 1:
-        try:
-            out["extras"] = {"codec_encoder": codec_encoder_probe(dev)}
-        except Exception as e:  # the headline line must survive whatever happens here
-            out["extras"] = {"codec_encoder": {"error": repr(e)[:200]}}
+        out["extras"] = {}
+        for name, probe in (("codec_encoder", codec_encoder_probe), ("speaker_encoder", speaker_encoder_probe)):
+            try:
+                out["extras"][name] = probe(dev)
+            except Exception as e:  # the headline line must survive whatever happens here
+                out["extras"][name] = {"error": repr(e)[:200]}
     if rank == 0:
         sys.stdout.flush()
         print(json.dumps(out), flush=True)
