@@ -9,9 +9,11 @@ quotes the metric on (config[2]: Qwen3-TTS-12Hz-1.7B CustomVoice, batch 8, non-s
 metric = speech tokens (12.5 Hz frames; x16 for individual codebook tokens) per second, whole job.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-N > 1 is launched by torchrun (one rank per GPU, independent replicas = weak scaling, NCCL only for the
-barrier / max-over-ranks reduction).  `--impl reference` times the reference's CPU path (oracle port driving
-the restated loop — the HF generate loop cannot run under transformers 5.5.0) on the host cores.
+N > 1 is launched by torchrun (one rank per GPU, full replica each; the request list is sharded and the waveforms
+gathered by qwen3_tts_b200.parallel.run_data_parallel; `value` is the weak view — B utterances per GPU — and
+`strong_scaling` the fixed-global-batch-32 view).  `--impl reference` times the reference's own modules
+(baseline/_ref, installed by baseline/install_reference.sh) on the host cores, driven by the restated generation
+loop (its HF generate() cannot run under transformers 5.5.0); see baseline/ref_arm.py.
 """
 import argparse
 import json
@@ -24,12 +26,18 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line (NCCL_DEBUG=VERSION prints a banner to stdout)
+# NCCL's communicator / topology lines are wanted (the driver reads them), stdout must stay the single JSON line:
+# INFO level, written to stderr
+os.environ.setdefault("NCCL_DEBUG", "INFO")
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 FRAME_SEC = 0.08
+METRIC = "speech_tokens_per_s"
+UNIT = "frames/s (12.5 Hz speech tokens; x16 codebook tokens)"   # ONE string for both arms: the driver divides them
+CPU_BUDGET_S = 200.0   # wall-clock target of a whole `--impl reference` run
 
 
 def usable_cores():
@@ -62,7 +70,9 @@ def parse():
     ap.add_argument("--model", default="1.7b", choices=["1.7b", "0.6b", "tiny"])
     ap.add_argument("--greedy", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-frames", type=int, default=2)
+    ap.add_argument("--cpu-frames", type=int, default=0, help="frame-steps per CPU sample (0 = sized from the time budget)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the side measurements (other batch sizes, 0.6B, encoders)")
+    ap.add_argument("--no-parity-check", action="store_true")
     return ap.parse_args()
 
 
@@ -142,28 +152,16 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_step(Wcpu, Ccpu, ocfg, ccfg, embs, trail, pad, sp_kwargs, n_frames, full_frames):
-    """One bounded sample of the workload on the host: prefill + n_frames frame-steps + codec decode of n_frames
-    frames, extrapolated to the full `full_frames` utterance.  Returns (frames_per_s, detail)."""
-    from oracle import talker as OT, codec as OC
-    e32 = [e.float() for e in embs]
-    t32 = [t.float() for t in trail]
-    sp0 = OT.SamplingCfg(max_new_tokens=1, suppress_eos=True, **sp_kwargs)
-    t0 = time.perf_counter()
-    OT.generate(Wcpu, ocfg, e32, t32, pad.float(), sp0)
-    t_pre = time.perf_counter() - t0
-    spn = OT.SamplingCfg(max_new_tokens=n_frames + 1, suppress_eos=True, **sp_kwargs)
-    t0 = time.perf_counter()
-    r = OT.generate(Wcpu, ocfg, e32, t32, pad.float(), spn)
-    t_all = time.perf_counter() - t0
-    per_frame = max(t_all - t_pre, 1e-9) / n_frames
-    codes = torch.stack(r.codes).transpose(1, 2).contiguous()  # (B,16,n)
-    t0 = time.perf_counter()
-    OC.decoder_forward(Ccpu, ccfg, codes)
-    t_codec = (time.perf_counter() - t0) / n_frames
-    B = len(embs)
-    total = t_pre + full_frames * (per_frame + t_codec)
-    return B * full_frames / total, {"prefill_s": t_pre, "per_frame_s": per_frame, "codec_per_frame_s": t_codec}
+def make_reference_arm(cfg, ccfg, W_bf16_cpu, CW_cpu, ncores):
+    """The reference's own modules (baseline/_ref, through the shims) or, if they cannot be imported, the oracle port."""
+    import contextlib
+    from baseline import ref_arm
+    Wcpu = {k: v.float().cpu() for k, v in W_bf16_cpu.items()}
+    Ccpu = {k: v.to(torch.bfloat16).float().cpu() for k, v in CW_cpu.items()}
+    ocfg, occfg = to_oracle_cfgs(cfg, ccfg)
+    with contextlib.redirect_stdout(sys.stderr):  # the reference's import-time chatter must not reach stdout
+        arm = ref_arm.ReferenceArm(ocfg, occfg, Wcpu, Ccpu, ncores)
+    return arm
 
 
 def to_oracle_cfgs(cfg, ccfg):
@@ -246,6 +244,103 @@ def speaker_encoder_probe(dev):
     return res
 
 
+def cpu_sample(arm, embs, trail, pad, spk, B, frames, n_first, plan_steps=0, budget_s=None):
+    """Bounded sample of the workload on the host: prefill (measured once) + frame-steps + codec decode of them.
+    With plan_steps > 0 the frames per step are sized so that plan_steps steps fit `budget_s`."""
+    from baseline import ref_arm
+    t_pre = arm.start(embs, trail, pad, spk)
+    timing, _ = arm.step_frames(n_first)
+    per = float(np.median(timing["frames"])) + timing["codec"] / n_first
+    n = n_first
+    if plan_steps > 0:
+        n = int(max(1, min(16, (budget_s - t_pre - per * n_first) / max(plan_steps * per, 1e-9))))
+    rate, det = ref_arm.workload_rate(timing, B, frames)
+    return rate, det, timing, n
+
+
+def parity_self_check(eng, cfg, W, embs, trail, pad, dev, frames=4):
+    """Teacher-forced check of THIS workload on THIS engine before anything is timed: the oracle (fp32, same
+    bf16-rounded weights) generates `frames` greedy frames from the bench prompts; the engine is forced along the same
+    codes and every talker / code-predictor logits row must agree within the parity tolerance of tests/test_gpu_ar.py."""
+    from oracle import talker as OT
+    from tests import helpers as Hh
+    import qwen3_tts_b200 as q
+    ocfg, _ = to_oracle_cfgs(cfg, q.CodecConfig())
+    Wf = {k: v.float().cpu() for k, v in W.items()}
+    osp = OT.SamplingCfg(do_sample=False, subtalker_dosample=False, max_new_tokens=frames + 1, suppress_eos=True)
+    t0 = time.perf_counter()
+    ref = OT.generate(Wf, ocfg, [e.float() for e in embs], [t.float() for t in trail], pad.float(), osp, record_logits=True)
+    forced = torch.stack(ref.codes).numpy()
+    sp = q.SamplingParams(do_sample=False, subtalker_dosample=False, max_new_tokens=frames + 1, suppress_eos=True)
+    codes, tl, cl, prog = Hh.run_engine_forced(eng.ar, [e.to(dev) for e in embs], [t.to(dev) for t in trail], pad.to(dev), sp, forced, dev)
+    G = cfg.num_code_groups
+    worst, worst_mean = 0.0, 0.0
+    for f in range(frames + 1):
+        r = ref.record["talker_logits"][f]
+        d = np.abs(tl[f] - r) / float(np.std(r))
+        worst, worst_mean = max(worst, float(d.max())), max(worst_mean, float(d.mean()))
+    for f in range(frames):
+        for j in range(G - 1):
+            r = ref.record["cp_logits"][f * (G - 1) + j]
+            d = np.abs(cl[f, j] - r) / float(np.std(r))
+            worst, worst_mean = max(worst, float(d.max())), max(worst_mean, float(d.mean()))
+    ok = bool(prog[0] == frames and (codes == forced).all() and worst < 0.2 and worst_mean < 0.05)
+    return {"ok": ok, "frames": frames, "rows": int(len(embs)), "max_abs_err_over_std": worst, "max_mean_err_over_std": worst_mean,
+            "tolerance": "max < 0.2 std, mean < 0.05 std (oracle's own bf16-vs-fp32 gap: 0.11 / 0.024)", "oracle_s": time.perf_counter() - t0}
+
+
+def decode_probe(eng, q, cfg, args, spk, B, N, dev, greedy=False):
+    """Device-resident prefill + N frame-steps + codec decode at batch B on an existing engine (side measurement)."""
+    class A:
+        batch = B
+    lens, embs, trail, pad = workload(A, cfg.talker.hidden_size)
+    kw = dict(do_sample=False, subtalker_dosample=False) if greedy else spk
+    sp = q.SamplingParams(max_new_tokens=N + 1, suppress_eos=True, seed=1234, **kw)
+    d_embs, d_trail, d_pad = [e.to(dev) for e in embs], [t.to(dev) for t in trail], pad.to(dev)
+    G = cfg.num_code_groups
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    res = []
+    for i in range(3):
+        e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+        e0.record()
+        eng.ar.prefill(d_embs, d_trail, d_pad, sp)
+        codes = torch.zeros(B, N, G, dtype=torch.int32, device=dev)
+        e1.record()
+        eng.ar.decode(N, codes)
+        e2.record()
+        eng.codec.chunked_decode(codes.transpose(1, 2))
+        e3.record()
+        torch.cuda.synchronize()
+        res.append((e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3)))
+    pre, dec, cod = res[-1]
+    tot = pre + dec + cod
+    # first packet: prefill + 4 frame-steps + codec of them, host in / host out
+    sp_fp = q.SamplingParams(max_new_tokens=5, suppress_eos=True, seed=1234, **kw)
+    fp = None
+    try:
+        for _ in range(2):
+            next(iter(eng.stream_synthesize(embs, trail, pad, sp_fp, packet_frames=4)))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            next(iter(eng.stream_synthesize(embs, trail, pad, sp_fp, packet_frames=4)))
+        fp = (time.perf_counter() - t0) / 3 * 1000.0
+    except Exception as e:
+        print(f"[bench] first-packet probe (B={B}) failed: {e!r}", file=sys.stderr)
+    S_mean = int(np.mean(lens) + N / 2)
+    a_bytes, _ = eng.ar.algorithmic_bytes(B, S_mean)
+    return {"batch": B, "frames": N, "sampling": "greedy" if greedy else "do_sample", "frames_per_s": B * N / (tot / 1000.0),
+            "rtf": (tot / 1000.0) / (B * N * FRAME_SEC), "ms_prefill": pre, "ms_decode": dec, "ms_codec": cod,
+            "ms_per_frame_step": dec / N, "first_packet_ms": fp, "roofline_frac_decode": a_bytes / (dec / N / 1000.0) / 1e9 / hbm_peak()[0]}
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -268,30 +363,45 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        t_begin = time.perf_counter()
         torch.set_num_threads(ncores)
         Wg = synthetic.random_tts_weights(cfg, device="cpu", seed=0, dtype=torch.bfloat16)
-        Wcpu = {k: v.float() for k, v in Wg.items()}
-        Ccpu = {k: v.to(torch.bfloat16).float() for k, v in synthetic.random_codec_weights(ccfg, device="cpu", seed=0).items()}
-        ocfg, occfg = to_oracle_cfgs(cfg, ccfg)
-        vals = []
-        t_begin = time.perf_counter()
-        for i in range(args.warmup + args.steps):
-            v, det = cpu_reference_step(Wcpu, Ccpu, ocfg, occfg, embs, trail, pad, spk, args.cpu_frames, args.frames)
-            if i >= args.warmup:
-                vals.append(v)
-        wall = time.perf_counter() - t_begin
-        val = float(np.mean(vals))
-        sample = (f"per step: prefill B={args.batch} + {args.cpu_frames} frame-steps + codec decode of {args.cpu_frames} frames, "
-                  f"fp32, {ncores} threads, extrapolated to {args.frames} frames")
-        out = {"impl": "reference", "metric": "speech_tokens_per_s", "value": val, "unit": "frames/s (12.5 Hz speech tokens)",
+        CWg = synthetic.random_codec_weights(ccfg, device="cpu", seed=0)
+        arm = make_reference_arm(cfg, ccfg, Wg, CWg, ncores)
+        del Wg, CWg
+        t_build = time.perf_counter() - t_begin
+        n_steps = args.warmup + args.steps
+        # warm-up step 1 = prefill (measured once) + 1 frame-step; it sizes the frames per step for the budget
+        _, _, tim0, n = cpu_sample(arm, embs, trail, pad, spk, args.batch, args.frames, 1, plan_steps=max(n_steps - 1, 1),
+                                   budget_s=max(CPU_BUDGET_S - t_build, 30.0))
+        if args.cpu_frames > 0:
+            n = args.cpu_frames
+        from baseline import ref_arm
+        frame_times, codec_per_frame = [], []
+        for i in range(1, args.warmup):
+            arm.step_frames(n)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            tim, _ = arm.step_frames(n)
+            frame_times += tim["frames"]
+            codec_per_frame.append(tim["codec"] / n)
+        elapsed = time.perf_counter() - t0
+        pooled = {"prefill": arm.t_prefill, "frames": frame_times, "codec": float(np.median(codec_per_frame)) * len(frame_times)}
+        val, det = ref_arm.workload_rate(pooled, args.batch, args.frames)
+        sample = (f"prefill of B={args.batch} measured once ({arm.t_prefill:.2f} s); each timed step = {n} consecutive frame-steps of the "
+                  f"running batch (15 code-predictor forwards + sampling + 1 talker step each) + chunked_decode of those {n} frames; "
+                  f"value = B*{args.frames} / (prefill + {args.frames} x (median frame-step + codec per frame)) over "
+                  f"{len(frame_times)} measured frame-steps; fp32, {ncores} threads; ms_per_step is the elapsed time of a timed step")
+        out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT,
                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": 1000.0 * args.batch * args.frames / val, "higher_is_better": True, "scaling": "weak",
+               "ms_per_step": 1000.0 * elapsed / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_block(args, lens, 1),
-               "rtf": 1.0 / (val * FRAME_SEC) * 1.0,
-               "cpu_baseline": {"value": val, "unit": "frames/s", "cores": ncores, "kind": "port", "sample": sample, **det},
-               "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-               "gpu_launches": 0, "wall_s": wall}
-        print(json.dumps(out))
+               "rtf": 1.0 / (val * FRAME_SEC),
+               "cpu_baseline": {"value": val, "unit": UNIT, "cores": ncores, "kind": arm.kind, "sample": sample,
+                                "frames_per_step": n, **det},
+               "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "gpu_launches": 0, "wall_s": time.perf_counter() - t_begin, "build_s": t_build}
+        print(json.dumps(out), flush=True)
         return
 
     # ------------------------------------------------------------------ B200 arm
@@ -303,11 +413,15 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(dev))
+    from qwen3_tts_b200 import parallel
     from qwen3_tts_b200.pipeline import TTSEngine
-    W = synthetic.random_tts_weights(cfg, device=dev, seed=0)
-    CW = synthetic.random_codec_weights(ccfg, device=dev, seed=0)
+    # weights are made on the CPU (seeded) and copied: the first kernels of this process are the engine's own
+    W = synthetic.random_tts_weights(cfg, device="cpu", seed=0)
+    CW = synthetic.random_codec_weights(ccfg, device="cpu", seed=0)
+    big = (rank == 0 and world == 1 and not args.no_extras) or world > 1
+    max_batch = max(args.batch, 32 if big else 1)
     max_ctx = max(lens) + args.frames + 8
-    eng = TTSEngine(cfg, W, ccfg, CW, device=dev, max_batch=max(args.batch, 1), max_ctx=max_ctx,
+    eng = TTSEngine(cfg, W, ccfg, CW, device=dev, max_batch=max_batch, max_ctx=max_ctx,
                     codec_max_frames=max(args.frames + 8, 64))
     sp = q.SamplingParams(max_new_tokens=args.frames + 1, suppress_eos=True, seed=1234, **spk)
     B, N, G = args.batch, args.frames, cfg.num_code_groups
@@ -315,6 +429,13 @@ def main():
     d_trail = [t.to(dev) for t in trail]
     d_pad = pad.to(dev)
     stream = torch.cuda.current_stream()
+
+    # ---- parity first: the exact engine / kernel instantiation that is timed below, against the oracle
+    parity = None
+    if rank == 0 and world == 1 and not args.no_parity_check:
+        parity = parity_self_check(eng, cfg, W, embs, trail, pad, dev)
+        if not parity["ok"]:
+            raise SystemExit(f"bench.py: parity self-check failed: {json.dumps(parity)}")
 
     def barrier():
         torch.cuda.synchronize()
@@ -358,17 +479,27 @@ def main():
     assert fd == N and all(v == N for v in n_valid), (fd, n_valid)
     assert torch.isfinite(wav).all()
 
-    # ---- end-to-end through the public call: pinned host inputs, H2D + D2H inside the timed region
+    # ---- end-to-end through the public calls: pinned host inputs, H2D + D2H inside the timed region.  The global
+    # request list (B per GPU) goes through parallel.run_data_parallel: shard -> synthesize -> gather of waveforms
+    requests = []
+    for r in range(world):
+        requests += list(zip(embs, trail))
+
+    def serve(reqs):
+        wavs, _ = eng.synthesize([e for e, _ in reqs], [t for _, t in reqs], pad, sp)
+        return wavs
+
     for _ in range(2):
-        eng.synthesize(embs, trail, pad, sp)
+        parallel.run_data_parallel(serve, requests)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        wavs_host, _ = eng.synthesize(embs, trail, pad, sp)
+        wavs_host = parallel.run_data_parallel(serve, requests)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    assert len(wavs_host) == world * B and all(w.shape == (N * 1920,) for w in wavs_host)
     h2d = sum(e.numel() * 2 for e in embs) + pad.numel() * 2
-    d2h = sum(w.size * 4 for w in wavs_host)
+    d2h = sum(w.size * 4 for w in wavs_host[:B])
 
     # ---- first-packet latency (config[3]): prefill + 4 frame-steps + codec decode of the 4 frames, host in / host out
     sp_fp = q.SamplingParams(max_new_tokens=5, suppress_eos=True, seed=1234, **spk)
@@ -384,6 +515,30 @@ def main():
         first_packet_ms = None
         print(f"[bench] first-packet probe failed: {e!r}", file=sys.stderr)
 
+    # ---- strong-scaling view: a FIXED global batch of 32 utterances split over the N GPUs
+    strong = None
+    if world > 1:
+        class A32:
+            batch = 32
+        l32, e32, t32, _ = workload(A32, H)
+        req32 = list(zip(e32, t32))
+        try:
+            for _ in range(2):
+                parallel.run_data_parallel(serve, req32)
+            barrier()
+            t0 = time.perf_counter()
+            reps = max(2, args.steps // 2)
+            for _ in range(reps):
+                w32 = parallel.run_data_parallel(serve, req32)
+            torch.cuda.synchronize()
+            strong_s = parallel.max_over_ranks((time.perf_counter() - t0) / reps, device=dev)
+            strong = {"global_batch": 32, "per_gpu_batch": 32 // world if 32 % world == 0 else f"{32 // world}-{32 // world + 1}",
+                      "value": 32 * N / strong_s, "unit": UNIT, "ms": strong_s * 1e3,
+                      "what": "host inputs -> run_data_parallel(shard, synthesize, all_gather_object of waveforms) -> host outputs"}
+            assert len(w32) == 32
+        except Exception as e:
+            strong = {"error": repr(e)[:200]}
+
     tms = torch.tensor([ms_total, e2e_s * 1000.0, t_dec], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -396,53 +551,67 @@ def main():
     S_mean = int(np.mean(lens) + N / 2)
     a_bytes, a_stream = eng.ar.algorithmic_bytes(B, S_mean)
     t_step = (t_dec / args.steps) / N / 1000.0  # s per frame-step (this rank)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak = 6650.0; peak_src = "fallback 6.65 TB/s (B200_PROFILING.md)"
+    peak, peak_src = hbm_peak()
     achieved = a_bytes / t_step / 1e9
     # measured DRAM traffic of this kernel from the committed `ncu --set full` capture (profiles/): bytes per
-    # frame-step of the B=8 capture (16 frame-steps per launch) scaled to this launch's frame count; null otherwise
-    traffic = None
+    # frame-step of the B=8 capture scaled to this launch's frame count; null when no capture of this round exists
+    traffic, traffic_src = None, None
     try:
         if args.batch == 8 and args.model == "1.7b":
-            txt = open(os.path.join(ROOT, "profiles", "r01_decode_kernel_ncu_full.txt")).read()
-            rd = float(re.search(r"^dram__bytes_read\.sum,([0-9.]+),Gbyte", txt, re.M).group(1)) * 1e9
-            wr = float(re.search(r"^dram__bytes_write\.sum,([0-9.]+),Mbyte", txt, re.M).group(1)) * 1e6
-            traffic = (rd + wr) / 16.0 * N
+            meta = json.load(open(os.path.join(ROOT, "profiles", "r02_decode_kernel_traffic.json")))
+            traffic = float(meta["dram_bytes_per_frame_step"]) * N
+            traffic_src = meta["source"]
     except Exception:
         traffic = None
-    roof = {"bound": "hbm", "kernel": "q3_program_kernel (fused frame-step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
-            "traffic_source": "profiles/r01_decode_kernel_ncu_full.txt (ncu --set full, per frame-step x frames)" if traffic else None,
+    roof = {"bound": "hbm", "kernel": "q3_step_kernel (fused frame-step)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
             "algorithmic_bytes_per_launch": a_bytes * N, "algorithmic_bytes_per_frame_step": a_bytes,
             "no_residency_bytes_per_frame_step": a_stream, "ms_per_frame_step": t_step * 1e3, "mean_context": S_mean}
 
-    out = {"metric": "speech_tokens_per_s", "value": value, "unit": "frames/s (12.5 Hz speech tokens; x16 codebook tokens)",
+    out = {"metric": METRIC, "value": value, "unit": UNIT,
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
            "config": config_block(args, lens, world), "rtf": (ms_total / 1000.0) / (frames_total * FRAME_SEC),
            "breakdown_ms_per_step": {"prefill": t_pre / args.steps, "decode": t_dec / args.steps, "codec": t_cod / args.steps},
            "roofline": roof, "first_packet_ms": first_packet_ms,
-           "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                   "rtf": (e2e_ms / 1000.0) / (frames_total * FRAME_SEC)},
-           "gpu_launches": args.steps * (cfg.talker.num_layers * 8 + 2 + eng.codec.last_launches()),  # prefill (7 GEMM/row kernels + attention per layer) + head + fused decode + codec
-           "clocks": clk}
+           "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "rtf": (e2e_ms / 1000.0) / (frames_total * FRAME_SEC),
+                   "path": "parallel.run_data_parallel(TTSEngine.synthesize): pinned host embeddings in, host waveforms out"},
+           "gpu_launches": args.steps * (cfg.talker.num_layers * 8 + 4 + eng.codec.last_launches()),  # prefill (7 GEMM/row kernels + attention per layer, index + gather) + head + fused decode + codec
+           "clocks": clk, "parity_check": parity, "strong_scaling": strong}
 
     # ---- reference CPU path beside it (rank 0, N=1 only): bounded sample on the host cores
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        torch.set_num_threads(ncores)
-        Wcpu = {k: v.float().cpu() for k, v in W.items()}
-        Ccpu = {k: v.to(torch.bfloat16).float().cpu() for k, v in CW.items()}
-        ocfg, occfg = to_oracle_cfgs(cfg, ccfg)
-        v, det = cpu_reference_step(Wcpu, Ccpu, ocfg, occfg, embs, trail, pad, spk, args.cpu_frames, N)
-        out["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": ncores, "kind": "port",
-                               "sample": f"prefill B={B} + {args.cpu_frames} frame-steps + codec decode of {args.cpu_frames} frames, "
-                                         f"fp32, {ncores} threads, extrapolated to {N} frames", **det}
-    # ---- side measurement, never part of `value`: the codec ENCODER (BASELINE config 1's encode half)
-    if rank == 0 and world == 1:
+        arm = make_reference_arm(cfg, ccfg, W, CW, ncores)
+        nfr = args.cpu_frames if args.cpu_frames > 0 else 4
+        v, det, _, _ = cpu_sample(arm, embs, trail, pad, spk, B, N, nfr)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": ncores, "kind": arm.kind,
+                               "sample": f"prefill of B={B} + {nfr} frame-steps + chunked_decode of those {nfr} frames, fp32, {ncores} threads; "
+                                         f"value = B*{N} / (prefill + {N} x (median frame-step + codec per frame))", **det}
+        del arm
+    # ---- side measurements, never part of `value`
+    if rank == 0 and world == 1 and not args.no_extras:
         out["extras"] = {}
+        for name, fn in (("batch1", lambda: decode_probe(eng, q, cfg, args, spk, 1, N, dev)),
+                         ("batch32", lambda: decode_probe(eng, q, cfg, args, spk, 32, N, dev)),
+                         ("batch8_first_packet", lambda: {"first_packet_ms": first_packet_ms})):
+            try:
+                out["extras"][name] = fn()
+            except Exception as e:
+                out["extras"][name] = {"error": repr(e)[:200]}
+        if args.model == "1.7b":
+            try:  # BASELINE config[1]: 0.6B, single utterance, greedy
+                eng.close()
+                del eng
+                torch.cuda.empty_cache()
+                c06 = model_cfg("0.6b")
+                e06 = TTSEngine(c06, synthetic.random_tts_weights(c06, device="cpu", seed=0), ccfg, CW, device=dev, max_batch=8,
+                                max_ctx=max_ctx, codec_max_frames=max(args.frames + 8, 64))
+                out["extras"]["0.6b_greedy_batch1"] = decode_probe(e06, q, c06, args, spk, 1, N, dev, greedy=True)
+                out["extras"]["0.6b_batch8"] = decode_probe(e06, q, c06, args, spk, 8, N, dev)
+                e06.close()
+            except Exception as e:
+                out["extras"]["0.6b"] = {"error": repr(e)[:200]}
         for name, probe in (("codec_encoder", codec_encoder_probe), ("speaker_encoder", speaker_encoder_probe)):
             try:
                 out["extras"][name] = probe(dev)

@@ -82,8 +82,14 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
-    if not os.path.exists(path) or os.environ.get("Q3_REBUILD"):
-        path = _build.build()
+    try:
+        # no-op when lib/build.stamp matches the digest of csrc/ + include/ + flags; rebuilds a stale or missing .so
+        path = _build.build(force=bool(os.environ.get("Q3_REBUILD")))
+    except Exception as e:
+        if not os.path.exists(path):
+            raise
+        import warnings
+        warnings.warn(f"qwen3tts_b200: could not rebuild ({e!r}); loading the existing {path}", RuntimeWarning)
     try:
         import torch  # noqa: F401  (makes sure libcudart.so.12 is already mapped)
     except Exception:

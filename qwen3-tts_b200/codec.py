@@ -30,6 +30,7 @@ class CodecDecoder:
         if self.device.type != "cuda":
             raise RuntimeError("CodecDecoder needs a CUDA device (no CPU fallback)")
         self.max_frames = max_frames
+        self.max_batch = int(max_batch)
         cc = _lib.CodecCfg()
         for n in ("codebook_size", "codebook_dim", "hidden_size", "latent_dim", "num_heads", "num_kv_heads", "head_dim",
                   "sliding_window", "intermediate_size", "num_layers", "num_quantizers", "decoder_dim"):

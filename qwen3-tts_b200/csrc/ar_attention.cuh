@@ -10,7 +10,7 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // one warp normalises + rotates one 128-vector; lane owns dims {l, l+32, l+64, l+96}
 __device__ __noinline__ void norm_rope_vec(const bf16* src, const bf16* nw, float eps, const bf16* cosr, const bf16* sinr,
-                                           float* out_f32, bf16* out_bf16) {
+                                           float* out_f32, bf16* out_bf16, bf16* out_bf16_b = nullptr) {
   const int lane = threadIdx.x & 31;
   float x[4], w[4];
 #pragma unroll
@@ -33,8 +33,74 @@ __device__ __noinline__ void norm_rope_vec(const bf16* src, const bf16* nw, floa
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     if (out_f32) out_f32[lane + 32 * i] = o[i];
-    else out_bf16[lane + 32 * i] = f2bf(o[i]);
+    else {
+      out_bf16[lane + 32 * i] = f2bf(o[i]);
+      if (out_bf16_b) out_bf16_b[lane + 32 * i] = f2bf(o[i]);
+    }
   }
+}
+
+// ---- unit geometry: one (sequence, kv head, context split) per CTA-iteration
+struct AttnUnit {
+  int seq, kvh, sp, nsplit, q0, nq, qstride, ctx_end, s0, s1;
+};
+
+__device__ __forceinline__ int attn_nsplit(const Phase& ph, const KParams& P, const StackDev& S, int frame) {
+  if (ph.seqmode != SEQ_DECODE) return 1;
+  int cmax = 0;
+  for (int b = 0; b < P.B; ++b) cmax = max(cmax, P.len0[b]);
+  cmax += frame + 1;
+  const int byctx = (cmax + 127) >> 7;
+  const int bygrid = (int)gridDim.x / (P.B * S.nkv);
+  return max(1, min(min(byctx, bygrid), MAXSPLIT));
+}
+
+__device__ __forceinline__ AttnUnit attn_unit(const Phase& ph, const KParams& P, const StackDev& S, int frame, int nsplit, int unit) {
+  AttnUnit u;
+  u.nsplit = nsplit;
+  u.sp = unit % nsplit;
+  u.kvh = (unit / nsplit) % S.nkv;
+  const int si = unit / (nsplit * S.nkv);
+  u.seq = si; u.q0 = si;
+  if (ph.seqmode == SEQ_CP) { u.nq = ph.nq; u.qstride = P.B; u.ctx_end = ph.ctx_end; }
+  else { u.nq = 1; u.qstride = 0; u.ctx_end = P.len0[si] + frame + 1; }
+  const int SL = (u.ctx_end + nsplit - 1) / nsplit;
+  u.s0 = u.sp * SL;
+  u.s1 = min(u.ctx_end, u.s0 + SL);
+  return u;
+}
+
+constexpr int KVWIN = 96;                                   // cached K/V rows per unit held in shared memory
+constexpr int ATT_QS_BYTES = 2 * RMAX * HD * 4;             // fp32 queries [nq<=2][RMAX][128]
+constexpr int ATT_RED_BYTES = 32 * RMAX * 130 * 4;          // per-half-warp partials
+constexpr int ATT_WIN_OFF = ATT_QS_BYTES + ATT_RED_BYTES;   // K window, then V window (bf16 [KVWIN][128] each)
+static_assert(ATT_WIN_OFF % 16 == 0 && ATT_WIN_OFF + 2 * KVWIN * HD * 2 <= ATT_SMEM, "attention shared-memory layout");
+
+// K/V rows [s0, min(s1, first new position, s0+KVWIN)) of `unit` -> the shared-memory window, asynchronously
+// (cp.async, L2 -> smem).  They were written in earlier phases, so this runs BEFORE the grid barrier that
+// precedes the attention phase: by the time q/k of the new token are normalised the cached rows are on chip.
+__device__ __forceinline__ void attn_window_issue(const Phase& ph, const KParams& P, unsigned char* smem, int frame, int unit) {
+  const StackDev& S = ph.stack == 0 ? P.talker : P.cp;
+  const int nsplit = attn_nsplit(ph, P, S, frame);
+  if (unit < P.B * S.nkv * nsplit) {
+    const AttnUnit u = attn_unit(ph, P, S, frame, nsplit, unit);
+    const int hi = min(min(u.s1, u.ctx_end - u.nq), u.s0 + KVWIN);
+    const int n = hi - u.s0;
+    const size_t base = ((((size_t)u.seq * S.layers + ph.layer) * S.nkv + u.kvh) * (size_t)S.cap + u.s0) * HD;
+    const char* kg = reinterpret_cast<const char*>(S.kc + base);
+    const char* vg = reinterpret_cast<const char*>(S.vc + base);
+    const uint32_t kw = smem_addr(smem + ATT_WIN_OFF), vw = kw + KVWIN * HD * 2;
+#pragma unroll 1
+    for (int c = threadIdx.x; c < n * 16; c += NTHREADS) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(kw + c * 16), "l"(kg + (size_t)c * 16) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vw + c * 16), "l"(vg + (size_t)c * 16) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__device__ __noinline__ void attn_prefetch(const Phase& ph, const KParams& P, unsigned char* smem, int frame) {
+  attn_window_issue(ph, P, smem, frame, (int)blockIdx.x);
 }
 
 __device__ __noinline__ void attn_phase(const Phase& ph, const KParams& P, unsigned char* smem, int frame) {
@@ -44,36 +110,27 @@ __device__ __noinline__ void attn_phase(const Phase& ph, const KParams& P, unsig
   const int R = nh / nkv;  // <= RMAX
   const int B = P.B;
   const int qkv_ld = (nh + 2 * nkv) * HD;
-  const int seqmode = ph.seqmode, layer = ph.layer;
-  const int nseq = B;
+  const int layer = ph.layer;
   const float eps = S.eps;
   const bf16 *qn = ph.qn, *kn = ph.kn;
-
-  int nsplit = 1;
-  if (seqmode == SEQ_DECODE) {
-    int cmax = 0;
-    for (int b = 0; b < B; ++b) cmax = max(cmax, P.len0[b]);
-    cmax += frame + 1;
-    const int byctx = (cmax + 127) >> 7;
-    const int bygrid = (int)gridDim.x / (B * nkv);
-    nsplit = max(1, min(min(byctx, bygrid), MAXSPLIT));
-  }
-  const int units = nseq * nkv * nsplit;
+  const int nsplit = attn_nsplit(ph, P, S, frame);
+  const int units = B * nkv * nsplit;
 
   float* qs = reinterpret_cast<float*>(smem);                 // [nq<=2][RMAX][128]
   float* red = qs + 2 * RMAX * HD;                            // [32 halfwarps][RMAX][130]
+  bf16* kwin = reinterpret_cast<bf16*>(smem + ATT_WIN_OFF);   // [KVWIN][128]
+  bf16* vwin = kwin + KVWIN * HD;
   __shared__ int s_ticket;
 
 #pragma unroll 1
   for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
-    const int sp = unit % nsplit;
-    const int kvh = (unit / nsplit) % nkv;
-    const int si = unit / (nsplit * nkv);
-    int seq, q0, nq, qstride, ctx_end;
-    if (seqmode == SEQ_CP) { seq = si; q0 = si; nq = ph.nq; qstride = B; ctx_end = ph.ctx_end; }
-    else { seq = si; q0 = si; nq = 1; qstride = 0; ctx_end = P.len0[si] + frame + 1; }
-    const int SL = (ctx_end + nsplit - 1) / nsplit;
-    const int s0 = sp * SL, s1 = min(ctx_end, s0 + SL);
+    if (unit != (int)blockIdx.x) {  // later units of this CTA (B*nkv*nsplit > grid): fetch their window now
+      __syncthreads();
+      attn_window_issue(ph, P, smem, frame, unit);
+    }
+    const AttnUnit U = attn_unit(ph, P, S, frame, nsplit, unit);
+    const int sp = U.sp, kvh = U.kvh, seq = U.seq, q0 = U.q0, nq = U.nq, qstride = U.qstride, ctx_end = U.ctx_end;
+    const int s0 = U.s0, s1 = U.s1;
     bf16* kc = S.kc + (((size_t)seq * layers + layer) * nkv + kvh) * (size_t)cap * HD;
     bf16* vc = S.vc + (((size_t)seq * layers + layer) * nkv + kvh) * (size_t)cap * HD;
 
@@ -91,15 +148,21 @@ __device__ __noinline__ void attn_phase(const Phase& ph, const KParams& P, unsig
       if (which < R) {
         norm_rope_vec(base + (kvh * R + which) * HD, qn, eps, cosr, sinr, qs + (j * RMAX + which) * HD, nullptr);
       } else if (owner) {
+        const bool inwin = pos - s0 < KVWIN;  // the new row is used from shared memory by this very phase
         if (which == R) {
-          norm_rope_vec(base + (nh + kvh) * HD, kn, eps, cosr, sinr, nullptr, kc + (size_t)pos * HD);
+          norm_rope_vec(base + (nh + kvh) * HD, kn, eps, cosr, sinr, nullptr, kc + (size_t)pos * HD, inwin ? kwin + (pos - s0) * HD : nullptr);
         } else {
           const bf16* vsrc = base + (nh + nkv + kvh) * HD;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) vc[(size_t)pos * HD + lane + 32 * i] = ldcg_bf16(vsrc + lane + 32 * i);
+          for (int i = 0; i < 4; ++i) {
+            const bf16 vv = ldcg_bf16(vsrc + lane + 32 * i);
+            vc[(size_t)pos * HD + lane + 32 * i] = vv;
+            if (inwin) vwin[(pos - s0) * HD + lane + 32 * i] = vv;
+          }
         }
       }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __threadfence_block();
     __syncthreads();
     PROF_MARK(2);
@@ -131,8 +194,18 @@ __device__ __noinline__ void attn_phase(const Phase& ph, const KParams& P, unsig
         const int tk0 = tb + (lane >> 4), tk1 = tk0 + 2;
         uint4 kv[2], vv[2];
         kv[0] = kv[1] = vv[0] = vv[1] = make_uint4(0, 0, 0, 0);
-        if (tk0 < e1) { kv[0] = ldcg16(kc + (size_t)tk0 * HD + l16 * 8); vv[0] = ldcg16(vc + (size_t)tk0 * HD + l16 * 8); }
-        if (tk1 < e1) { kv[1] = ldcg16(kc + (size_t)tk1 * HD + l16 * 8); vv[1] = ldcg16(vc + (size_t)tk1 * HD + l16 * 8); }
+        if (tk0 < e1) {
+          if (tk0 - s0 < KVWIN) {
+            kv[0] = *reinterpret_cast<const uint4*>(kwin + (tk0 - s0) * HD + l16 * 8);
+            vv[0] = *reinterpret_cast<const uint4*>(vwin + (tk0 - s0) * HD + l16 * 8);
+          } else { kv[0] = ldcg16(kc + (size_t)tk0 * HD + l16 * 8); vv[0] = ldcg16(vc + (size_t)tk0 * HD + l16 * 8); }
+        }
+        if (tk1 < e1) {
+          if (tk1 - s0 < KVWIN) {
+            kv[1] = *reinterpret_cast<const uint4*>(kwin + (tk1 - s0) * HD + l16 * 8);
+            vv[1] = *reinterpret_cast<const uint4*>(vwin + (tk1 - s0) * HD + l16 * 8);
+          } else { kv[1] = ldcg16(kc + (size_t)tk1 * HD + l16 * 8); vv[1] = ldcg16(vc + (size_t)tk1 * HD + l16 * 8); }
+        }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {  // fully unrolled: register arrays must keep compile-time indices (no local memory)
           const bool valid = (u == 0 ? tk0 : tk1) < e1;

@@ -39,6 +39,7 @@ int q3_set_err(const char* fmt, ...) {
   return 1;
 }
 
+#include "ar_ring.cuh"
 #include "ar_program.cuh"
 #include "ar_gemv.cuh"
 #include "ar_attention.cuh"
@@ -50,22 +51,70 @@ namespace {
 // the persistent kernel
 // ------------------------------------------------------------------------------------------------
 template <int NT>
-__global__ void __launch_bounds__(NTHREADS, 1) q3_program_kernel(const __grid_constant__ KParams P) {
-  extern __shared__ __align__(128) unsigned char smem[];
+__global__ void __launch_bounds__(NTHREADS, 1) q3_step_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ Phase s_ph[2];
-  __shared__ uint4 s_nw[2][256];  // RMSNorm weights of the current / next GEMV phase (<= 2048 bf16)
+  __shared__ RoundTab s_tab;
   DevState* st = P.st;
-  unsigned int epoch = 0;  // host resets bar_count to 0 before every launch
-  if (threadIdx.x < (int)(sizeof(Phase) / 4))
-    reinterpret_cast<uint32_t*>(&s_ph[0])[threadIdx.x] = reinterpret_cast<const uint32_t*>(P.prog)[threadIdx.x];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool use_counter = (P.flags & 1) != 0;
+  unsigned int epoch = 0;  // host resets bar_count / bar_flags to 0 before every launch
+  PMeta* meta = reinterpret_cast<PMeta*>(smem + P.plan.meta_off);
+  const uint32_t bar0 = smem_addr(smem + P.plan.bar_off);       // [NWARPS][R] ring barriers, then the x barrier
+  const uint32_t xbar = bar0 + 8u * (NWARPS * P.plan.nslots);
+  uint32_t xpar = 0;
+  const int niter = P.mode == 1 ? P.max_iters : 1;
+
+  // ---- per-CTA phase metas: which contiguous weight bytes this CTA consumes in every phase
+#pragma unroll 1
+  for (int i = tid; i < P.n_phases; i += NTHREADS) {
+    const Phase* gp = P.prog + i;
+    PMeta m;
+    m.woff16 = 0; m.ntc = 0; m.kb = 0;
+    if (gp->type == PH_GEMV) {
+      int t0, ntc;
+      q3ring::cta_tiles(gp->tq, gp->tr, (int)blockIdx.x, t0, ntc);
+      m.ntc = (uint16_t)ntc;
+      m.kb = (uint16_t)gp->kb;
+      m.woff16 = (uint32_t)(((reinterpret_cast<const char*>(gp->w) - P.wbase) + (size_t)t0 * gp->kb * 1024) >> 4);
+    }
+    meta[i] = m;
+  }
+  if (tid == 0) {
+    for (int i = 0; i < NWARPS * P.plan.nslots + 1; ++i) mbar_init(bar0 + 8u * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
+    g_prof_row = nullptr;
+  }
+  if (tid < (int)(sizeof(Phase) / 4))
+    reinterpret_cast<uint32_t*>(&s_ph[0])[tid] = reinterpret_cast<const uint32_t*>(P.prog)[tid];
   __syncthreads();
-  if (s_ph[0].type == PH_GEMV && s_ph[0].norm_w != nullptr && (int)threadIdx.x < s_ph[0].kb * 4)
-    s_nw[0][threadIdx.x] = reinterpret_cast<const uint4*>(s_ph[0].norm_w)[threadIdx.x];
+  if (s_ph[0].type == PH_GEMV && s_ph[0].norm_w != nullptr && tid < s_ph[0].kb * 4)
+    reinterpret_cast<uint4*>(smem + P.plan.nw_off)[tid] = reinterpret_cast<const uint4*>(s_ph[0].norm_w)[tid];
+  if (s_ph[0].type == PH_ATTN) attn_prefetch(s_ph[0], P, smem + P.plan.x_off, st->step);  // (synthetic profiling programs only)
+
+  // L2 eviction priorities of the weight stream (createpolicy): the code predictor's layer weights are re-read on
+  // every one of its 15 passes -> keep a fraction that fits beside the talker stream; everything else streams
+  uint64_t pol_keep, pol_stream;
+  asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol_keep) : "f"(P.keep_fraction));
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  const int cp_phases = P.mode == 1 ? P.cp_phases : 0;
+
+  // ---- weight ring of this warp: start streaming before anything else happens
+  Ring rg;
+  q3ring::prod_init(rg.prod);
+  rg.SB = P.plan.slot_blocks; rg.R = P.plan.nslots;
+  rg.slots = smem_addr(smem + P.plan.ring_off) + (uint32_t)(warp * rg.R * rg.SB) * 1024u;
+  rg.bars = bar0 + 8u * (warp * rg.R);
+  rg.c_slot = 0; rg.c_par = 0; rg.p_slot = 0; rg.outstanding = 0;
+  q3ring::prod_next_run(rg.prod, meta, P.n_phases, niter, warp);
+#pragma unroll 1
+  for (int i = 0; i < rg.R; ++i) ring_produce(rg, meta, P, niter, warp, lane, pol_keep, pol_stream, cp_phases);
   __syncthreads();
+
   const int step_base = st->step;
   int iters_done = 0;
   int slot = 0;
-  const int niter = P.mode == 1 ? P.max_iters : 1;
 #pragma unroll 1
   for (int it = 0; it < niter; ++it) {
     const int frame = step_base + it;
@@ -80,42 +129,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) q3_program_kernel(const __grid_co
       // issued now into a register and only stored to smem after the body, so its L2 round trip is hidden.
       int nx = pi + 1;
       if (nx >= P.n_phases) nx = (P.mode == 1) ? 0 : -1;
-      const bool dhave = nx >= 0 && threadIdx.x < (int)(sizeof(Phase) / 4);
+      const bool dhave = nx >= 0 && tid < (int)(sizeof(Phase) / 4);
       uint32_t dreg = 0;
-      if (dhave) dreg = reinterpret_cast<const uint32_t*>(P.prog + nx)[threadIdx.x];
+      if (dhave) dreg = reinterpret_cast<const uint32_t*>(P.prog + nx)[tid];
       const Phase& ph = s_ph[slot];
-      if (threadIdx.x == 0) {
+      if (tid == 0) {
         g_prof_row = (P.prof && it == 0) ? P.prof + ((size_t)pi * gridDim.x + blockIdx.x) * 8 : nullptr;
         PROF_MARK(6);
       }
       const int type = ph.type;
-      if (type == PH_GEMV) gemv_phase<NT>(ph, P, smem, s_nw[slot]);
-      else if (type == PH_ATTN) attn_phase(ph, P, smem, frame);
-      else sample_phase(ph, P, smem, frame, P.mode == 0);
-      if (dhave) reinterpret_cast<uint32_t*>(&s_ph[slot ^ 1])[threadIdx.x] = dreg;
-      __syncthreads();
-      // pull the next GEMV's weight slice toward L2 while the barrier drains, and fetch its norm weights (the
-      // load is issued before the barrier, the smem store happens after it: zero exposed latency)
+      if (type == PH_GEMV) gemv_phase<NT>(ph, meta[pi], P, rg, meta, niter, smem, &s_tab, xbar, xpar, pol_keep, pol_stream, cp_phases);
+      else if (type == PH_ATTN) attn_phase(ph, P, smem + P.plan.x_off, frame);
+      else sample_phase(ph, P, smem + P.plan.x_off, frame, P.mode == 0);
+      if (dhave) reinterpret_cast<uint32_t*>(&s_ph[slot ^ 1])[tid] = dreg;
+      __syncthreads();  // body done (global writes of every thread precede thread 0's release), next descriptor visible
+      PROF_MARK(0);
+      grid_arrive(st, epoch, use_counter);
+      // work that does not depend on the other CTAs, between arrive and wait: the next GEMV's RMSNorm weights
+      // (load now, store after the wait) and the KV rows the next attention phase will need
       uint4 nwv = make_uint4(0, 0, 0, 0);
       bool nw_have = false;
       if (nx >= 0) {
         const Phase& nph = s_ph[slot ^ 1];
-        if (!(P.dbg_skip & 32)) prefetch_phase_weights(nph);
-        if (!(P.dbg_skip & 64) && nph.type == PH_GEMV && nph.norm_w != nullptr && (int)threadIdx.x < nph.kb * 4) {
-          nwv = reinterpret_cast<const uint4*>(nph.norm_w)[threadIdx.x];
+        if (nph.type == PH_GEMV && nph.norm_w != nullptr && tid < nph.kb * 4) {
+          nwv = reinterpret_cast<const uint4*>(nph.norm_w)[tid];
           nw_have = true;
+        } else if (nph.type == PH_ATTN) {
+          attn_prefetch(nph, P, smem + P.plan.x_off, pi + 1 >= P.n_phases ? frame + 1 : frame);
         }
       }
-      PROF_MARK(0);
-      grid_barrier(st, epoch);
+      grid_wait(st, epoch, use_counter);
       slot ^= 1;
-      if (nw_have) s_nw[slot][threadIdx.x] = nwv;  // visible to the next phase after its first __syncthreads... see below
+      if (nw_have) reinterpret_cast<uint4*>(smem + P.plan.nw_off)[tid] = nwv;
       __syncthreads();
       PROF_MARK(1);
     }
     ++iters_done;
   }
-  if (P.mode == 1 && blockIdx.x == 0 && threadIdx.x == 0) st->step = step_base + iters_done;
+  // never leave with bulk copies in flight into this CTA's shared memory
+#pragma unroll 1
+  while (rg.outstanding > 0) {
+    mbar_wait(rg.bars + 8u * rg.c_slot, (uint32_t)rg.c_par, st);
+    ring_release(rg);
+  }
+  if (P.mode == 1 && blockIdx.x == 0 && tid == 0) st->step = step_base + iters_done;
 }
 
 }  // namespace
@@ -157,7 +214,12 @@ struct q3_engine {
   int prog_cap = 0;
   // programs (host copies) for the current batch size
   int prog_B = -1;
-  int dbg_skip = 0;
+  int flags = 0;              // Q3_FLAGS / q3_debug_set_skip: A/B knobs of the frame-step kernel (see KParams.flags)
+  const char* wbase = nullptr;  // lowest packed-weight address (PMeta offsets)
+  float keep_fraction = 0.5f;
+  int cp_phases = 0;
+  int nt_frame = 1, nt_head = 1, max_dyn_smem = 0;
+  SmemPlan plan_frame{}, plan_head{};
   bool use_proj_tab = true;   // Q3_CP_PROJ_TAB=0 keeps the projection GEMV in passes >= 1 (A/B knob)
   bf16* proj_tab = nullptr;   // small_to_mtp_projection(cp.codec_embedding) [(G-1)*Vc][Hc], built once at finalize
   std::vector<Phase> prog_layers, prog_head, prog_frame;
@@ -178,10 +240,19 @@ struct q3_engine {
     void* q = nullptr;
     cudaError_t e = cudaMalloc(&q, count * sizeof(T));
     if (e != cudaSuccess) return q3_set_err("cudaMalloc(%zu B) failed: %s", count * sizeof(T), cudaGetErrorString(e));
-    cudaMemset(q, 0, count * sizeof(T));
+    // zero-fill ordered against everything else this engine does: same stream as the pack / copy work, then wait
+    // (allocation is a load-time or growth-time event; nothing on the per-step path allocates)
+    cudaMemsetAsync(q, 0, count * sizeof(T), copy_stream);
+    cudaStreamSynchronize(copy_stream);
     allocs.push_back(q);
     *p = reinterpret_cast<T*>(q);
     return 0;
+  }
+  void release(void* q) {
+    if (!q) return;
+    for (size_t i = 0; i < allocs.size(); ++i)
+      if (allocs[i] == q) { allocs.erase(allocs.begin() + i); break; }
+    cudaFree(q);
   }
 };
 
@@ -213,8 +284,8 @@ extern "C" int q3_engine_create(const q3_engine_cfg* cfg, q3_engine** out) {
     Q3_REQUIRE(s->hidden_size % 32 == 0 && s->intermediate_size % 32 == 0 && s->vocab_size % 16 == 0,
                "hidden/intermediate must be multiples of 32 and vocab of 16");
     Q3_REQUIRE(s->num_heads % s->num_kv_heads == 0 && s->num_heads / s->num_kv_heads <= RMAX, "GQA group (heads / kv_heads) must be <= 2");
-    Q3_REQUIRE(xs_stride_bytes(s->hidden_size) * MAXCOLS <= XS_BYTES && xs_stride_bytes(s->num_heads * HD) * MAXCOLS <= XS_BYTES,
-               "hidden_size / num_heads*head_dim above 2048 unsupported");
+    Q3_REQUIRE(xs_stride_bytes(s->hidden_size) * MAXCOLS <= x_budget_nt(4) && s->hidden_size <= 2048,
+               "hidden_size above 2048 unsupported");
   }
   Q3_REQUIRE(cfg->has_cp_projection || cfg->talker.hidden_size == cfg->cp.hidden_size,
              "Identity projection requires equal hidden sizes");
@@ -242,9 +313,10 @@ extern "C" int q3_engine_create(const q3_engine_cfg* cfg, q3_engine** out) {
   if (e->alloc(&e->tts_pad, (size_t)H)) return 1;
   if (e->alloc(&e->seen, (size_t)MAXB * cfg->talker.vocab_size)) return 1;
   if (e->alloc(&e->split_buf, (size_t)MAXB * cfg->talker.num_kv_heads * MAXSPLIT * RMAX * 130)) return 1;
-  e->smem_bytes = smem_bytes_nt(4);
-  static_assert(SAMPLER_SMEM <= ATT_SMEM, "sampler must fit the minimum shared-memory request");
-  Q3_REQUIRE(e->smem_bytes <= (size_t)prop.sharedMemPerBlockOptin, "not enough shared memory per block");
+  static_assert(SAMPLER_SMEM <= X_MIN_BYTES && ATT_SMEM <= X_MIN_BYTES, "attention / sampler scratch must fit the x area");
+  Q3_REQUIRE((size_t)SMEM_OPTIN <= (size_t)prop.sharedMemPerBlockOptin, "not enough shared memory per block");
+  if (const char* f = getenv("Q3_FLAGS")) e->flags = atoi(f);
+  if (const char* f = getenv("Q3_KEEP_FRACTION")) e->keep_fraction = (float)atof(f);
   *out = e;
   return 0;
 }
@@ -267,6 +339,9 @@ static bool is_gemv_weight(const std::string& n) {
 extern "C" int q3_engine_load_tensor(q3_engine* e, const char* name, const void* dev, int64_t rows, int64_t cols) {
   Q3_REQUIRE(e && name && dev, "null argument");
   Q3_CUDA(cudaSetDevice(e->cfg.device));
+  // `dev` may still be being produced on the caller's stream (a cat / cast queued by the framework): the ABI has
+  // no stream argument here, so wait for the device once per tensor — a load-time cost only
+  Q3_CUDA(cudaDeviceSynchronize());
   std::string n(name);
   if (is_gemv_weight(n)) {
     Q3_REQUIRE(rows % 16 == 0 && cols % 32 == 0, "%s: GEMV weight must be [16a][32b], got [%lld][%lld]", name,
@@ -350,6 +425,43 @@ static int add_layers(q3_engine* e, std::vector<Phase>& prog, const char* pfx, S
   return 0;
 }
 
+// Shared-memory plan of one program at one batch class (layout: ar_program.cuh).  Marks every GEMV phase as staged
+// (activations copied to the x area once, B fragments read from shared memory) or not (B fragments straight from L2:
+// only inputs that do not fit, i.e. K = intermediate_size at B > 8).
+static int make_smem_plan(q3_engine* e, std::vector<Phase>& prog, int B, int nt, SmemPlan* out) {
+  const int budget = x_budget_nt(nt);
+  int xneed = X_MIN_BYTES;
+  for (Phase& p : prog) {
+    if (p.type != PH_GEMV) continue;
+    const int nc = p.ncmode == NC_B ? B : 2 * B;
+    const int need = xs_stride_bytes(p.kb * 32) * ((nc + 7) / 8 * 8);
+    p.staged = need <= budget ? 1 : 0;
+    Q3_REQUIRE(p.staged || p.norm_w == nullptr, "normed GEMV input of %d columns x K=%d does not fit the x area", nc, p.kb * 32);
+    if (p.staged) xneed = std::max(xneed, need);
+  }
+  SmemPlan pl{};
+  auto up = [](int v, int a) { return (v + a - 1) / a * a; };
+  pl.x_off = 0; pl.x_bytes = up(xneed, 1024);
+  pl.part_off = pl.x_off + pl.x_bytes;
+  pl.nw_off = pl.part_off + part_bytes_nt(nt);
+  pl.ring_off = up(pl.nw_off + NW_BYTES, 1024);
+  const int meta_bytes = up((int)prog.size() * (int)sizeof(q3ring::PMeta), 16);
+  const int bar_bytes = 8 * (NWARPS * MAX_SLOTS + 1) + 8;
+  const int avail = e->max_dyn_smem - pl.ring_off - meta_bytes - bar_bytes;
+  pl.slot_blocks = 0;
+  for (int sb : {4, 2, 1}) {
+    const int r = avail / (NWARPS * sb * 1024);
+    if (r >= 2) { pl.slot_blocks = sb; pl.nslots = std::min(r, MAX_SLOTS); break; }
+  }
+  Q3_REQUIRE(pl.slot_blocks > 0, "no shared memory left for the weight rings (x area %d B, batch class %d)", pl.x_bytes, nt);
+  pl.meta_off = pl.ring_off + NWARPS * pl.nslots * pl.slot_blocks * 1024;
+  pl.bar_off = pl.meta_off + meta_bytes;
+  pl.total = pl.bar_off + bar_bytes;
+  Q3_REQUIRE(pl.total <= e->max_dyn_smem, "shared-memory plan of %d B exceeds %d B", pl.total, e->max_dyn_smem);
+  *out = pl;
+  return 0;
+}
+
 static int build_programs(q3_engine* e, int B) {
   if (e->prog_B == B) return 0;
   const q3_engine_cfg& c = e->cfg;
@@ -415,6 +527,7 @@ static int build_programs(q3_engine* e, int B) {
     Phase s{}; s.type = PH_SAMPLE; s.group = j + 1;
     F.push_back(s);
   }
+  e->cp_phases = (int)F.size();
   if (add_layers(e, F, "talker", T, T.h, NC_B, SEQ_DECODE, 1, 0)) return 1;
   F.push_back(gemv(whead, T.h, H, tnorm, T.eps, T.logits, T.vocab, EPI_LOGITS, NC_B, nullptr, e->past_hidden));
   {
@@ -424,9 +537,18 @@ static int build_programs(q3_engine* e, int B) {
   for (std::vector<Phase>* pv : {&e->prog_layers, &e->prog_head, &e->prog_frame})
     for (Phase& p : *pv)
       if (p.type == PH_GEMV) { p.tq = p.n_tiles / e->sm_count; p.tr = p.n_tiles % e->sm_count; }
-  // upload
+  // shared-memory plans: which phases stage their activations, how large the x area is, what is left for the rings
+  e->nt_frame = (joint ? 2 * B : B) <= 8 ? 1 : (joint ? 2 * B : B) <= 16 ? 2 : 4;
+  e->nt_head = B <= 8 ? 1 : B <= 16 ? 2 : 4;
+  if (make_smem_plan(e, e->prog_head, B, e->nt_head, &e->plan_head) || make_smem_plan(e, e->prog_frame, B, e->nt_frame, &e->plan_frame))
+    return 1;
+  Q3_REQUIRE((int)F.size() <= MAX_PHASES, "frame program has %d phases (max %d)", (int)F.size(), MAX_PHASES);
+  // upload (a batch-size change is rare: wait for launches that may still walk the old program)
+  Q3_CUDA(cudaDeviceSynchronize());
   const size_t total = e->prog_layers.size() + e->prog_head.size() + F.size();
   if ((int)total > e->prog_cap) {
+    e->release(e->prog_dev);
+    e->prog_dev = nullptr;
     if (e->alloc(&e->prog_dev, total + 64)) return 1;
     e->prog_cap = (int)total + 64;
   }
@@ -477,11 +599,31 @@ extern "C" int q3_engine_finalize(q3_engine* e) {
     if (gemm_launch(plan, e->copy_stream)) return 1;
     Q3_CUDA(cudaStreamSynchronize(e->copy_stream));
   }
+  // kernel attributes: all opt-in shared memory minus the kernel's static part is the dynamic budget of the plans
+  {
+    int stat = 0;
+    for (const void* fn : {(const void*)q3_step_kernel<1>, (const void*)q3_step_kernel<2>, (const void*)q3_step_kernel<4>}) {
+      cudaFuncAttributes fa;
+      Q3_CUDA(cudaFuncGetAttributes(&fa, fn));
+      stat = std::max(stat, (int)fa.sharedSizeBytes);
+    }
+    e->max_dyn_smem = SMEM_OPTIN - (stat + 127) / 128 * 128;
+    Q3_CUDA(cudaFuncSetAttribute(q3_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_dyn_smem));
+    Q3_CUDA(cudaFuncSetAttribute(q3_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_dyn_smem));
+    Q3_CUDA(cudaFuncSetAttribute(q3_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_dyn_smem));
+  }
+  {  // weight arena base for the 32-bit (x16 B) offsets of the phase metas
+    const char *lo = nullptr, *hi = nullptr;
+    for (auto& kv : e->packed) {
+      const char* a = reinterpret_cast<const char*>(kv.second.w);
+      const char* b = a + (size_t)kv.second.n * kv.second.k * 2;
+      if (!lo || a < lo) lo = a;
+      if (!hi || b > hi) hi = b;
+    }
+    Q3_REQUIRE(lo && (size_t)(hi - lo) < ((size_t)1 << 36), "packed weights span more than 64 GB of address space");
+    e->wbase = lo;
+  }
   if (build_programs(e, 1)) return 1;
-  // kernel attributes
-  Q3_CUDA(cudaFuncSetAttribute(q3_program_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_nt(1)));
-  Q3_CUDA(cudaFuncSetAttribute(q3_program_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_nt(2)));
-  Q3_CUDA(cudaFuncSetAttribute(q3_program_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_nt(4)));
   // algorithmic bytes
   auto lw = [](const q3_stack_cfg& s) {
     return (double)s.hidden_size * (s.num_heads * HD) * 2 + 2.0 * s.hidden_size * (s.num_kv_heads * HD) +
@@ -494,11 +636,14 @@ extern "C" int q3_engine_finalize(q3_engine* e) {
   e->w_talker_bytes = 2.0 * wt;
   e->w_cp_unique_bytes = 2.0 * (cpl + proj + heads);
   e->w_cp_stream_bytes = 2.0 * ((c.num_code_groups - 1) * (cpl + proj) + heads);
+  // L2 residency of the code predictor's layer weights (re-read on each of its passes): keep ~80 MB of them at
+  // evict_last priority beside the talker's evict_first stream (126 MB L2)
+  if (!getenv("Q3_KEEP_FRACTION")) e->keep_fraction = (float)std::min(1.0, 80e6 / (2.0 * cpl));
   e->finalized = true;
   return 0;
 }
 
-static int launch_program(q3_engine* e, int off, int n, int mode, int max_iters, int nt,
+static int launch_program(q3_engine* e, int off, int n, int mode, int max_iters, int nt, const SmemPlan& plan,
                           int* codes_dev, cudaStream_t stream) {
   KParams P{};
   P.prog = e->prog_dev + off; P.n_phases = n; P.mode = mode; P.max_iters = max_iters; P.st = e->st;
@@ -511,12 +656,15 @@ static int launch_program(q3_engine* e, int off, int n, int mode, int max_iters,
   if (e->proj_tab) { P.cp_next = e->proj_tab; P.cp_next_dst = e->cp.h; P.cp_next_w = e->cfg.cp.hidden_size; }
   else { P.cp_next = P.emb_cp; P.cp_next_dst = P.x_cp; P.cp_next_w = e->cfg.talker.hidden_size; }
   P.tts_pad = e->tts_pad; P.seen = e->seen; P.codes_out = codes_dev; P.codes_stride = e->codes_stride;
-  P.split_buf = e->split_buf; P.forced = e->forced; P.n_forced = e->n_forced; P.dbg_tlogits = e->dbg_t; P.dbg_clogits = e->dbg_c; P.prof = (mode == 1) ? e->prof : nullptr; P.dbg_skip = e->dbg_skip;
-  Q3_CUDA(cudaMemsetAsync(&e->st->bar_count, 0, sizeof(unsigned int), stream));
+  P.split_buf = e->split_buf; P.forced = e->forced; P.n_forced = e->n_forced; P.dbg_tlogits = e->dbg_t; P.dbg_clogits = e->dbg_c; P.prof = (mode == 1) ? e->prof : nullptr;
+  P.flags = e->flags; P.wbase = e->wbase; P.keep_fraction = e->keep_fraction;
+  P.plan = plan; P.cp_phases = (off == e->off_frame && n == (int)e->prog_frame.size()) ? e->cp_phases : 0;
+  Q3_REQUIRE(n <= MAX_PHASES, "program of %d phases exceeds %d", n, MAX_PHASES);
+  Q3_CUDA(cudaMemsetAsync(&e->st->bar_count, 0, sizeof(unsigned int) * (1 + 256), stream));  // counter + per-CTA flags
   void* args[] = {&P};
-  const void* fn = nt == 1 ? (const void*)q3_program_kernel<1> : nt == 2 ? (const void*)q3_program_kernel<2>
-                                                                        : (const void*)q3_program_kernel<4>;
-  Q3_CUDA(cudaLaunchCooperativeKernel(fn, dim3(e->sm_count), dim3(NTHREADS), args, (size_t)smem_bytes_nt(nt), stream));
+  const void* fn = nt == 1 ? (const void*)q3_step_kernel<1> : nt == 2 ? (const void*)q3_step_kernel<2>
+                                                                     : (const void*)q3_step_kernel<4>;
+  Q3_CUDA(cudaLaunchCooperativeKernel(fn, dim3(e->sm_count), dim3(NTHREADS), args, (size_t)plan.total, stream));
   return 0;
 }
 
@@ -550,6 +698,8 @@ extern "C" int q3_prefill(q3_engine* e, int32_t B, const void* embeds_dev, const
   if (trailing_stride > 0 && trailing_dev) {
     const size_t need = (size_t)MAXB * trailing_stride * H;
     if (need > e->trailing_alloc) {  // (re)allocate the engine-owned copy of trailing_text_hidden
+      Q3_CUDA(cudaStreamSynchronize(stream));  // growth only: earlier launches may still read the old buffer
+      e->release(e->trailing);
       if (e->alloc(&e->trailing, need)) return 1;
       e->trailing_alloc = need;
     }
@@ -559,26 +709,24 @@ extern "C" int q3_prefill(q3_engine* e, int32_t B, const void* embeds_dev, const
   e->codes_stride = 0;
   e->frames_issued = 0;
   // ---- prefill on tensor cores: all prompt tokens of all rows at once (packed [ntok][H], rows back to back)
-  int ntok = 0;
-  std::vector<int> hseq, hpos, last(B);
-  for (int b = 0; b < B; ++b) {
-    for (int p = 0; p < lens_host[b]; ++p) { hseq.push_back(b); hpos.push_back(p); }
-    ntok += lens_host[b];
-    last[b] = ntok - 1;
-  }
+  PfLens pl{};
+  pl.B = B;
+  for (int b = 0; b < B; ++b) pl.start[b + 1] = pl.start[b] + lens_host[b];
+  const int ntok = pl.start[B];
   const q3_stack_cfg& tc = e->cfg.talker;
   const int nh = tc.num_heads, nkv = tc.num_kv_heads, I = tc.intermediate_size, QKV = (nh + 2 * nkv) * HD;
   if (ntok > e->pf_cap) {
-    const int cap = std::max(ntok, 1024);
+    const int cap = std::max(ntok + ntok / 4, 1024);
+    Q3_CUDA(cudaStreamSynchronize(stream));  // growth only
+    for (void* q : {(void*)e->pf_x, (void*)e->pf_xn, (void*)e->pf_qkv, (void*)e->pf_attn, (void*)e->pf_act, (void*)e->pf_seq, (void*)e->pf_pos})
+      e->release(q);
     if (e->alloc(&e->pf_x, (size_t)cap * H) || e->alloc(&e->pf_xn, (size_t)cap * H) || e->alloc(&e->pf_qkv, (size_t)cap * QKV) ||
         e->alloc(&e->pf_attn, (size_t)cap * nh * HD) || e->alloc(&e->pf_act, (size_t)cap * I) || e->alloc(&e->pf_seq, (size_t)cap) ||
         e->alloc(&e->pf_pos, (size_t)cap))
       return 1;
     e->pf_cap = cap;
   }
-  Q3_CUDA(cudaMemcpyAsync(e->pf_seq, hseq.data(), (size_t)ntok * sizeof(int), cudaMemcpyHostToDevice, stream));
-  Q3_CUDA(cudaMemcpyAsync(e->pf_pos, hpos.data(), (size_t)ntok * sizeof(int), cudaMemcpyHostToDevice, stream));
-  Q3_CUDA(cudaStreamSynchronize(stream));  // hseq/hpos are stack-owned pageable buffers
+  pf_index_kernel<<<(ntok + 255) / 256, 256, 0, stream>>>(pl, e->pf_seq, e->pf_pos);
   Q3_CUDA(cudaMemcpyAsync(e->pf_x, embeds_dev, (size_t)ntok * H * 2, cudaMemcpyDeviceToDevice, stream));
   const int mt = (ntok + 127) / 128;
   const int zero = 0;
@@ -608,11 +756,9 @@ extern "C" int q3_prefill(q3_engine* e, int32_t B, const void* embeds_dev, const
     { GemmEpilogue ep{}; ep.resid = e->pf_x; ep.out_raw = e->pf_x; if (gemm(e->pf_act, I, p + ".down", H, ep)) return 1; }
   }
   Q3_CUDA(cudaGetLastError());
-  for (int b = 0; b < B; ++b)
-    Q3_CUDA(cudaMemcpyAsync(e->h_last + (size_t)b * H, e->pf_x + (size_t)last[b] * H, (size_t)H * 2, cudaMemcpyDeviceToDevice, stream));
+  pf_gather_last_kernel<<<B, 128, 0, stream>>>(pl, e->pf_x, e->h_last, H);
   // head + sample codebook-0 of frame 0 (codes are materialised by q3_decode's first call via st->c0)
-  const int nt_head = B <= 8 ? 1 : B <= 16 ? 2 : 4;
-  if (launch_program(e, e->off_head, (int)e->prog_head.size(), 0, 1, nt_head, nullptr, stream)) return 1;
+  if (launch_program(e, e->off_head, (int)e->prog_head.size(), 0, 1, e->nt_head, e->plan_head, nullptr, stream)) return 1;
   return 0;
 }
 
@@ -625,10 +771,7 @@ extern "C" int q3_decode(q3_engine* e, int32_t max_frames, int32_t* codes_dev, i
   Q3_REQUIRE(e->max_len0 + e->frames_issued + max_frames <= e->cfg.max_ctx, "KV capacity exceeded: prompt %d + %d frames > max_ctx %d",
              e->max_len0, e->frames_issued + max_frames, e->cfg.max_ctx);
   e->frames_issued += max_frames;
-  const int B = e->B;
-  const int cols = (2 * B <= MAXCOLS) ? 2 * B : B;
-  const int nt = cols <= 8 ? 1 : cols <= 16 ? 2 : 4;
-  return launch_program(e, e->off_frame, (int)e->prog_frame.size(), 1, max_frames, nt, codes_dev, stream);
+  return launch_program(e, e->off_frame, (int)e->prog_frame.size(), 1, max_frames, e->nt_frame, e->plan_frame, codes_dev, stream);
 }
 
 extern "C" int q3_get_progress(q3_engine* e, int32_t* frames_done, int32_t* n_valid, int32_t* finished) {
@@ -678,11 +821,13 @@ extern "C" int q3_describe_frame_program(q3_engine* e, int32_t* kinds, int32_t c
 
 // Debug/profiling: run a synthetic program made of `count` repetitions of the frame-program phases
 // [first, first+span) (mode 0, one pass) and return the elapsed device time.  Used by tools/icache_probe.py.
-extern "C" int q3_debug_set_skip(q3_engine* e, int32_t mask) { if (e) e->dbg_skip = mask; return 0; }
+// A/B knobs of the frame-step kernel (KParams.flags): 1 = counter barrier, 2 = LDG staging of un-normed inputs
+extern "C" int q3_debug_set_skip(q3_engine* e, int32_t mask) { if (e) e->flags = mask; return 0; }
 
 extern "C" int q3_debug_time_phases(q3_engine* e, int32_t first, int32_t span, int32_t count, float* ms_out, void* stream_) {
   Q3_REQUIRE(e && e->prog_B > 0 && e->B > 0, "prefill first");
   Q3_REQUIRE(first >= 0 && span >= 1 && first + span <= (int)e->prog_frame.size() && count >= 1, "bad phase range");
+  Q3_REQUIRE(count * span <= MAX_PHASES, "count*span must be <= %d", MAX_PHASES);
   cudaStream_t stream = (cudaStream_t)stream_;
   std::vector<Phase> prog;
   for (int i = 0; i < count; ++i)
@@ -697,14 +842,14 @@ extern "C" int q3_debug_time_phases(q3_engine* e, int32_t first, int32_t span, i
   Q3_CUDA(cudaMemcpy(dev, prog.data(), (size_t)n * sizeof(Phase), cudaMemcpyHostToDevice));
   Phase* saved = e->prog_dev;
   e->prog_dev = dev;
-  const int B = e->B;
-  const int cols = (2 * B <= MAXCOLS) ? 2 * B : B;
-  const int nt = cols <= 8 ? 1 : cols <= 16 ? 2 : 4;
+  const int nt = e->nt_frame;
+  SmemPlan plan;
+  int rc = make_smem_plan(e, prog, e->B, nt, &plan);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  int rc = launch_program(e, 0, n, 0, 1, nt, nullptr, stream);  // warm
+  if (!rc) rc = launch_program(e, 0, n, 0, 1, nt, plan, nullptr, stream);  // warm
   cudaEventRecord(e0, stream);
-  if (!rc) rc = launch_program(e, 0, n, 0, 1, nt, nullptr, stream);
+  if (!rc) rc = launch_program(e, 0, n, 0, 1, nt, plan, nullptr, stream);
   cudaEventRecord(e1, stream);
   cudaStreamSynchronize(stream);
   float ms = 0.f;

@@ -1,39 +1,75 @@
-// Grid barrier, block helpers and the GEMV phase (RMSNorm-fused activation staging, batch-in-N mma.sync, fused epilogues).
+// Grid barrier, mbarrier / TMA helpers, the per-warp weight ring and the GEMV phase (RMSNorm-fused activation staging,
+// batch-in-N mma.sync fed from shared memory, fused epilogues).
 // Part of the ar_engine.cu translation unit (include order: ar_program, ar_gemv, ar_attention, ar_sampler,
 // the persistent kernel in ar_engine.cu, ar_prefill).
 #pragma once
 
 namespace {
 
+using q3ring::PMeta;
+using q3ring::ProdIter;
+using q3ring::RunGeom;
+
 // ------------------------------------------------------------------------------------------------
-// grid barrier (monotonic counter; arrive = release, wait = acquire)
+// grid barrier.  Two interchangeable implementations (KParams.flags bit 0):
+//   flags  (default): every CTA owns one epoch word; arrive = st.release of the new epoch, wait = warp 0 polls all
+//                     gridDim words (5 coalesced lines) until none is behind.  No atomics, no single hot address.
+//   counter         : release-red on one counter + relaxed poll (round-1 barrier).
+// Polls are RELAXED on purpose: ld.acquire.gpu compiles to LDG.STRONG + CCTL.IVALL (a full L1 invalidation per
+// poll iteration).  Correctness does not need it: every cross-CTA read in this kernel is an L2 access
+// (ld.global.cg / cp.async.cg / cp.async.bulk), the writers released at gpu scope before their arrival became
+// visible, and the GPU does not speculate loads past the poll loop + bar.sync.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_barrier(DevState* st, unsigned int& epoch) {
-  __syncthreads();  // every thread's global writes happen-before thread 0's release (bar.sync is cumulative)
-  if (threadIdx.x == 0) {
-    epoch += gridDim.x;
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&st->bar_count) : "memory");
-    long long t0 = clock64();
-    unsigned int v;
-    while (true) {
-      // RELAXED poll on purpose: ld.acquire.gpu compiles to LDG.STRONG + CCTL.IVALL, i.e. it invalidates the whole
-      // L1 on every poll iteration (measured: ~55 invalidations per barrier), which evicts the stack / spill lines
-      // of all 16 warps and makes every phase start cold.  Correctness does not need the invalidation: every
-      // cross-CTA read in this kernel is an L2 load (ld.global.cg), the writers released at gpu scope before
-      // their arrival became visible, and the GPU does not speculate loads past this loop + bar.sync.
-      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&st->bar_count) : "memory");
-      if ((int)(v - epoch) >= 0) break;
-      if (clock64() - t0 > 8000000000LL) {  // ~4 s: never hang the box
-        st->error = 77;
-        __threadfence();
-        __trap();
-      }
-    }
-  }
-  __syncthreads();
+__device__ __forceinline__ void barrier_timeout(DevState* st) {
+  st->error = 77;
+  __threadfence();
+  __trap();
 }
 
-// fine-grained profiling marks (thread 0 of CTA 0 only, first frame of a profiled launch)
+__device__ __forceinline__ void grid_arrive(DevState* st, unsigned int& epoch, bool use_counter) {
+  // caller: __syncthreads() already executed (every thread's global writes happen-before thread 0's release)
+  if (threadIdx.x == 0) {
+    if (use_counter) {
+      epoch += gridDim.x;
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&st->bar_count) : "memory");
+    } else {
+      epoch += 1;
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&st->bar_flags[blockIdx.x]), "r"(epoch) : "memory");
+    }
+  }
+}
+
+__device__ __forceinline__ void grid_wait(DevState* st, unsigned int epoch, bool use_counter) {
+  if (use_counter) {
+    if (threadIdx.x == 0) {
+      const long long t0 = clock64();
+      unsigned int v;
+      while (true) {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&st->bar_count) : "memory");
+        if ((int)(v - epoch) >= 0) break;
+        if (clock64() - t0 > 8000000000LL) barrier_timeout(st);  // ~4 s: never hang the box
+      }
+    }
+  } else if (threadIdx.x < 32) {
+    const long long t0 = clock64();
+    const int n = (int)gridDim.x;
+    // thread 0 carries the epoch; broadcast it inside warp 0
+    const unsigned int ep = __shfl_sync(0xffffffffu, epoch, 0);
+    while (true) {
+      bool ok = true;
+#pragma unroll 1
+      for (int i = threadIdx.x; i < n; i += 32) {
+        unsigned int v;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&st->bar_flags[i]) : "memory");
+        ok = ok && ((int)(v - ep) >= 0);
+      }
+      if (__all_sync(0xffffffffu, ok)) break;
+      if (clock64() - t0 > 8000000000LL) barrier_timeout(st);
+    }
+  }
+}
+
+// fine-grained profiling marks (thread 0 only, first frame of a profiled launch)
 __shared__ unsigned long long* g_prof_row;
 #define PROF_MARK(k)                                                                   \
   do {                                                                                 \
@@ -44,11 +80,97 @@ __shared__ unsigned long long* g_prof_row;
     }                                                                                  \
   } while (0)
 
-// NOTE ON CODE SIZE: the frame program walks ~560 phases per frame-step, alternating between the three phase
-// bodies below.  Their combined hot code must stay inside the SM's ~32 KB instruction cache, otherwise every
-// phase re-fetches its instructions from L2 (measured: ~4 us of pure fetch stall per phase with 150 KB of code).
-// Hence: loops are rolled (#pragma unroll 1) wherever latency is not at stake, bulk data goes through shared
-// memory instead of unrolled register arrays, and there is no 64-bit division on the device.
+// ------------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy (TMA) primitives
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, DevState* st) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {  // protocol bug: report instead of hanging the box
+      st->error = 78;
+      __threadfence();
+      __trap();
+    }
+  }
+}
+// global -> shared bulk copy through the TMA unit; bytes % 16 == 0, both addresses 16-byte aligned.
+// `policy` is an L2 eviction-priority descriptor (createpolicy): weights that are re-read within a frame
+// (code predictor) are kept, the once-per-frame talker stream is marked evict-first.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_plain(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-warp weight ring: the warp's lane 0 is the producer (cp.async.bulk into the warp's private slots), the whole
+// warp is the consumer.  Producer and consumer walk the same deterministic piece sequence (ar_ring.cuh); the
+// producer stays up to R pieces ahead, across phases and grid barriers, so weight streaming never waits for the
+// dependency chain of the activations.
+// ------------------------------------------------------------------------------------------------
+struct Ring {
+  ProdIter prod;
+  uint32_t slots;      // shared address of this warp's first slot
+  uint32_t bars;       // shared address of this warp's first full-barrier
+  int SB, R;           // blocks per slot, slots
+  int c_slot, c_par;   // consumer position / parity of the current lap
+  int p_slot;          // producer position
+  int outstanding;     // pieces requested and not yet consumed
+};
+
+// one piece, if the ring has a free slot and the program has more work for this warp
+__device__ __forceinline__ void ring_produce(Ring& rg, const PMeta* meta, const KParams& P, int niter, int warp, int lane,
+                                             uint64_t pol_keep, uint64_t pol_stream, int cp_phases) {
+  if (rg.prod.done || rg.outstanding >= rg.R) return;
+  const int nb = q3ring::imin(rg.SB, rg.prod.u1 - rg.prod.u);
+  if (lane == 0) {
+    const uint32_t bar = rg.bars + 8u * rg.p_slot;
+    const uint32_t bytes = (uint32_t)nb << 10;
+    mbar_expect_tx(bar, bytes);
+    // phases [0, cp_phases) of the frame program are the code predictor: its 157 MB are re-read 15x per frame
+    bulk_g2s(rg.slots + (uint32_t)(rg.p_slot * rg.SB) * 1024u, P.wbase + q3ring::prod_piece_offset(rg.prod), bytes, bar,
+             rg.prod.pi < cp_phases ? pol_keep : pol_stream);
+  }
+  rg.prod.u += nb;
+  if (++rg.p_slot == rg.R) rg.p_slot = 0;
+  ++rg.outstanding;
+  if (rg.prod.u >= rg.prod.u1) q3ring::prod_next_run(rg.prod, meta, P.n_phases, niter, warp);
+}
+
+__device__ __forceinline__ void ring_release(Ring& rg) {
+  if (++rg.c_slot == rg.R) { rg.c_slot = 0; rg.c_par ^= 1; }
+  --rg.outstanding;
+}
 
 // ------------------------------------------------------------------------------------------------
 // block-wide helpers (NTHREADS threads)
@@ -81,30 +203,11 @@ __device__ __noinline__ int block_min_int(int v, int* red) {
 // ------------------------------------------------------------------------------------------------
 // GEMV phase:  dst[col][row] = epi( sum_k W[row][k] * x[col][k] )
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ int xs_stride_bytes(int K) { return ((K * 2 + 127) / 128) * 128 + 64; }
+__host__ __device__ __forceinline__ int xs_stride_bytes(int K) { return K * 2 + 64; }  // +64 B: conflict-free B-fragment reads
 
 __device__ __forceinline__ int phase_nc(int ncmode, const KParams& P) {
   const int B = P.B;
   return ncmode == NC_B ? B : 2 * B;
-}
-
-// balanced contiguous split of a phase's row tiles over the CTAs (tq/tr precomputed on the host)
-__device__ __forceinline__ void cta_tiles(int tq, int tr, int& t0, int& ntc) {
-  const int c = blockIdx.x;
-  t0 = c * tq + min(c, tr);
-  ntc = tq + (c < tr ? 1 : 0);
-}
-
-__device__ __forceinline__ void prefetch_phase_weights(const Phase& ph) {
-  if (ph.type != PH_GEMV) return;
-  int t0, ntc;
-  cta_tiles(ph.tq, ph.tr, t0, ntc);
-  const unsigned int bytes = (unsigned int)ntc * (unsigned int)ph.kb * 1024u;
-  const unsigned int off = threadIdx.x * 32768u;
-  if (off < bytes) {
-    const char* base = reinterpret_cast<const char*>(ph.w) + (size_t)t0 * ph.kb * 1024;
-    l2_prefetch_bulk(base + off, min(32768u, bytes - off));
-  }
 }
 
 __device__ __forceinline__ uint32_t norm_pair(uint32_t x2, uint32_t w2, float inv) {
@@ -114,9 +217,9 @@ __device__ __forceinline__ uint32_t norm_pair(uint32_t x2, uint32_t w2, float in
 }
 
 // stage x (optionally RMS-normed) into smem as bf16 [col][K] (rows skewed by 64 B).  One warp per column; a lane
-// issues up to 8 independent 16-byte loads (K <= 2048 per pass) before touching the data; the RMSNorm runs on the
-// registers (sum of squares -> warp reduce -> scale) and the result is written to smem once.  The norm weights
-// were prefetched into nw_s one phase ahead (see the main loop), so they cost no global round trip here.
+// issues up to 8 independent 16-byte loads per pass before touching the data; the RMSNorm runs on the registers
+// (sum of squares -> warp reduce -> scale) and the result is written to smem once.  The norm weights sit in nw_s
+// (fetched before the preceding grid barrier).
 __device__ __forceinline__ void stage_columns(const bf16* __restrict__ src, int src_ld, bool normed, float eps,
                                               bf16* __restrict__ save, int K, int nc, char* __restrict__ xs, int xstride,
                                               const uint4* __restrict__ nw_s) {
@@ -146,7 +249,6 @@ __device__ __forceinline__ void stage_columns(const bf16* __restrict__ src, int 
           }
         }
         ss = warp_sum(ss);
-        PROF_MARK(7);
         const float inv = rsqrtf(ss / (float)K + eps);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -171,143 +273,188 @@ __device__ __forceinline__ void stage_columns(const bf16* __restrict__ src, int 
   }
 }
 
-constexpr int DEPTH = (NTHREADS <= 256) ? 8 : 4;  // k32-blocks (2 x 16 B per lane each) kept in flight per warp
+// per-CTA scratch of one GEMV round (shared memory): which warps hold partial sums of which tile
+struct RoundTab {
+  int tl0[NWARPS];   // first tile (round-local) of warp w's run
+  int wf[8], wl[8];  // first / last warp contributing to round-local tile tl
+};
 
-__device__ __forceinline__ void gemv_preload(uint4 (&a)[DEPTH][2], const uint4* __restrict__ wp, int nk) {
-#pragma unroll
-  for (int i = 0; i < DEPTH; ++i)
-    if (i < nk) { a[i][0] = ldg_stream(wp + i * 64); a[i][1] = ldg_stream(wp + i * 64 + 32); }
-}
-
-template <int NT, bool STAGED>
-__device__ __forceinline__ void gemv_segment(float (&acc)[NT][4], uint4 (&a)[DEPTH][2], const uint4* __restrict__ wp, int nk, int kb0,
-                                             const char* __restrict__ xs, int xstride, const bf16* __restrict__ src,
-                                             int src_ld, int nc, int g, int t) {
-  // rolling register pipeline: DEPTH k32-blocks (2 x 16 B per lane each) always in flight; a slot is refilled the
-  // moment it has been copied out, so no fragment is ever held twice
-#pragma unroll 1
-  for (int k0 = 0; k0 < nk; k0 += DEPTH) {
-#pragma unroll
-    for (int i = 0; i < DEPTH; ++i) {
-      if (k0 + i < nk) {
-        const int kb = kb0 + k0 + i;
-        const uint4 r = a[i][0], s = a[i][1];
-        if (k0 + i + DEPTH < nk) {
-          a[i][0] = ldg_stream(wp + (k0 + i + DEPTH) * 64);
-          a[i][1] = ldg_stream(wp + (k0 + i + DEPTH) * 64 + 32);
-        }
-#pragma unroll
-        for (int n = 0; n < NT; ++n) {
-          uint4 b;
-          const int col = n * 8 + g;
-          if (STAGED) {
-            b = *reinterpret_cast<const uint4*>(xs + (size_t)col * xstride + kb * 64 + t * 16);
-          } else {
-            b = (col < nc) ? ldcg16(src + (size_t)col * src_ld + kb * 32 + t * 8) : make_uint4(0, 0, 0, 0);
-          }
-          mma_bf16_16816(acc[n], r.x, s.x, r.y, s.y, b.x, b.y);
-          mma_bf16_16816(acc[n], r.z, s.z, r.w, s.w, b.z, b.w);
-        }
-      }
-    }
-  }
+__device__ __forceinline__ int idiv_small(int a, int b) {  // exact for 0 <= a < 2^20, 0 < b < 2^12
+  return __float2int_rz(__fdividef((float)a + 0.5f, (float)b));
 }
 
 template <int NT>
-__device__ __noinline__ void gemv_phase(const Phase& ph, const KParams& P, unsigned char* smem, const uint4* nw_s) {
+__device__ __forceinline__ void flush_acc(float (&acc)[2][NT][4], float* pp, int nct, int t, int g) {
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    if (n < nct) {
+      const int col = n * 8 + 2 * t;
+      pp[(col)*PCOL + g] = acc[0][n][0] + acc[1][n][0];
+      pp[(col + 1) * PCOL + g] = acc[0][n][1] + acc[1][n][1];
+      pp[(col)*PCOL + g + 8] = acc[0][n][2] + acc[1][n][2];
+      pp[(col + 1) * PCOL + g + 8] = acc[0][n][3] + acc[1][n][3];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[0][n][q] = acc[1][n][q] = 0.f;
+  }
+}
+
+// The phase body.  `m` is this CTA's meta of the phase (tiles owned, K blocks); the weights arrive through the ring.
+template <int NT>
+__device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const KParams& P, Ring& rg, const PMeta* meta, int niter,
+                                           unsigned char* smem, RoundTab* tab, uint32_t xbar, uint32_t& xpar,
+                                           uint64_t pol_keep, uint64_t pol_stream, int cp_phases) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  // descriptor fields -> registers once
-  const uint4* const wbase = ph.w;
-  const int KB = ph.kb, K = KB * 32, epi = ph.epi;
+  const int KB = m.kb, K = KB * 32, epi = ph.epi, ntc = m.ntc;
   const bf16* const src = ph.src;
   const int src_ld = ph.src_ld, dst_ld = ph.dst_ld;
-  const bf16* const norm_w = ph.norm_w;
+  const bool normed = ph.norm_w != nullptr;
   void* const dst = ph.dst;
-  const bf16* const bias = ph.bias;
   const int nc = phase_nc(ph.ncmode, P);
-  int t0, ntc;
-  cta_tiles(ph.tq, ph.tr, t0, ntc);
-  const int skip = P.dbg_skip;
-  if (skip & 16) return;
-
-  char* xs = reinterpret_cast<char*>(smem);
-  float* part = reinterpret_cast<float*>(smem + xs_bytes_nt(NT));  // [NWARPS][2][NT*8][PCOL]
-  const int xstride = xs_stride_bytes(K);
-  const bool staged = (norm_w != nullptr) || (xstride * (NT * 8) <= xs_bytes_nt(NT));
+  const int nct = (nc + 7) >> 3;
+  const bool staged = ph.staged != 0;
+  int t0, ntc_chk;
+  q3ring::cta_tiles(ph.tq, ph.tr, (int)blockIdx.x, t0, ntc_chk);
   bf16* const save = (ph.save_normed != nullptr && blockIdx.x == 0) ? ph.save_normed : nullptr;
-  // first weight fragments of this warp go in flight BEFORE the activations are staged (they do not depend on x)
-  uint4 afr[DEPTH][2];
-  const int TB0 = min(NWARPS, ntc);
-  const int upw0 = (TB0 * KB + NWARPS - 1) / NWARPS;
-  const bool have0 = ntc > 0 && warp * upw0 < TB0 * KB && !(skip & (8 | 2));
-  if (have0) {
-    const int u = warp * upw0, tl = u / KB, kb0 = u - tl * KB;
-    gemv_preload(afr, wbase + ((size_t)(t0 + tl) * KB + kb0) * 64 + lane, min(KB - kb0, min(TB0 * KB, u + upw0) - u));
+
+  char* xs = reinterpret_cast<char*>(smem + P.plan.x_off);
+  float* part = reinterpret_cast<float*>(smem + P.plan.part_off);  // [NWARPS][2][NT*8][PCOL]
+  const uint4* nw_s = reinterpret_cast<const uint4*>(smem + P.plan.nw_off);
+  const int xstride = xs_stride_bytes(K);
+  const uint32_t xs_sh = smem_addr(xs);
+
+  // ---- activations -> shared memory
+  if (staged && (ntc > 0 || save)) {
+    if (normed || (P.flags & 2)) {
+      stage_columns(src, src_ld, normed, ph.eps, save, K, nc, xs, xstride, nw_s);
+    } else {
+      // plain copy of nc contiguous rows: one bulk (TMA) copy per column, completion on the CTA's x barrier
+      if (tid == 0) {
+        asm volatile("fence.proxy.async;" ::: "memory");  // earlier generic accesses of the x area / of src's producers
+        mbar_expect_tx(xbar, (uint32_t)(nc * K * 2));
+#pragma unroll 1
+        for (int col = 0; col < nc; ++col)
+          bulk_g2s_plain(xs_sh + (uint32_t)(col * xstride), src + (size_t)col * src_ld, (uint32_t)(K * 2), xbar);
+      }
+      mbar_wait(xbar, xpar, P.st);
+      xpar ^= 1;
+    }
   }
   PROF_MARK(2);
-  if (staged && (ntc > 0 || save) && !(skip & 1)) stage_columns(src, src_ld, norm_w != nullptr, ph.eps, save, K, nc, xs, xstride, nw_s);
-  __syncthreads();
-  PROF_MARK(3);
-  if (ntc <= 0) return;
+  if (ntc <= 0) {
+    __syncthreads();
+    return;
+  }
 
+  const bool swiglu = epi == EPI_SWIGLU;
+  const int rsh = swiglu ? 3 : 4;  // output rows per tile: 8 (gate/up pairs) or 16
 #pragma unroll 1
-  for (int tb0 = 0; tb0 < ntc; tb0 += NWARPS) {
-    const int TB = min(NWARPS, ntc - tb0);
-    const int units = TB * KB;
-    const int upw = (units + NWARPS - 1) / NWARPS;
-    const int u1 = min(units, (warp + 1) * upw);
-    int seg = 0;
+  for (int round = 0; round * 8 < ntc; ++round) {
+    if (round) __syncthreads();  // the previous round's epilogue still reads the round table and part
+    const RunGeom rgm = q3ring::run_geom(ntc, KB, round, warp);
+    const int TB = rgm.TB, upw = rgm.upw;
+    const int tl0 = idiv_small(rgm.u0, KB);
+    if (tid < NWARPS) tab->tl0[tid] = idiv_small(q3ring::imin(TB * KB, tid * upw), KB);
+    else if (tid < NWARPS + 8 && tid - NWARPS < TB) {
+      const int tl = tid - NWARPS;
+      tab->wf[tl] = idiv_small(tl * KB, upw);
+      tab->wl[tl] = idiv_small((tl + 1) * KB - 1, upw);
+    }
+    // residual values of this thread's first two output elements (own rows: stable since the previous barrier)
+    int tbl = 0;
+    while ((1 << tbl) < TB) ++tbl;
+    const int nelem = nc << (rsh + tbl);
+    float resid[2] = {0.f, 0.f};
+    if (epi == EPI_RESID) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int e = tid + i * NTHREADS;
+        const int tl = (e >> rsh) & ((1 << tbl) - 1);
+        if (e < nelem && tl < TB) {
+          const int row = (t0 + round * 8 + tl) * 16 + (e & 15);
+          resid[i] = bf2f(ldcg_bf16(reinterpret_cast<const bf16*>(dst) + (size_t)(e >> (rsh + tbl)) * dst_ld + row));
+        }
+      }
+    }
+    __syncthreads();  // x area + round table visible (also separates rounds: part is free again)
+
+    // ---- main loop: this warp's run, piece by piece, out of its ring
+    {
+      float acc[2][NT][4];
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[0][n][q] = acc[1][n][q] = 0.f;
+      int u = rgm.u0;
+      int kbi = rgm.u0 - tl0 * KB;
+      int seg = 0;
+      float* pp = part + ((warp * 2) * (NT * 8)) * PCOL;
 #pragma unroll 1
-    for (int u = warp * upw; u < u1;) {
-      const int tl = u / KB;
-      const int kb0 = u - tl * KB;
-      const int nk = min(KB - kb0, u1 - u);
-      float acc[NT][4];
+      while (u < rgm.u1) {
+        const int nb = q3ring::imin(rg.SB, rgm.u1 - u);
+        uint4 bq[4][NT];
+        if (!staged) {  // B fragments straight from L2, issued before the slot wait
 #pragma unroll
-      for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-      const uint4* wp = wbase + ((size_t)(t0 + tb0 + tl) * KB + kb0) * 64 + lane;
-      if (!(skip & 2)) {
-      if (!(tb0 == 0 && seg == 0) || (skip & 8)) gemv_preload(afr, wp, nk);  // the very first segment was preloaded above
-      if (staged) gemv_segment<NT, true>(acc, afr, wp, nk, kb0, xs, xstride, src, src_ld, nc, g, t);
-      else gemv_segment<NT, false>(acc, afr, wp, nk, kb0, xs, xstride, src, src_ld, nc, g, t);
-      }
-      // spill partial sums: part[warp][seg][col][row]
-      float* pp = part + ((warp * 2 + seg) * (NT * 8)) * PCOL;
+          for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int n = 0; n < NT; ++n) {
-        const int col = n * 8 + 2 * t;
-        pp[(col)*PCOL + g] = acc[n][0];
-        pp[(col + 1) * PCOL + g] = acc[n][1];
-        pp[(col)*PCOL + g + 8] = acc[n][2];
-        pp[(col + 1) * PCOL + g + 8] = acc[n][3];
+            for (int n = 0; n < NT; ++n) {
+              const int col = n * 8 + g;
+              int kk = kbi + i;  // may run past KB at a tile boundary: wrap
+              if (kk >= KB) kk -= KB;
+              bq[i][n] = (i < nb && n < nct && col < nc) ? ldcg16(src + (size_t)col * src_ld + kk * 32 + t * 8) : make_uint4(0, 0, 0, 0);
+            }
+        }
+        mbar_wait(rg.bars + 8u * rg.c_slot, (uint32_t)rg.c_par, P.st);
+        const uint32_t sp = rg.slots + (uint32_t)(rg.c_slot * rg.SB) * 1024u + (uint32_t)lane * 16u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i < nb) {
+            const uint4 r = lds128(sp + i * 1024), s = lds128(sp + i * 1024 + 512);
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+              if (n < nct) {
+                uint4 b;
+                if (staged) b = lds128(xs_sh + (uint32_t)((n * 8 + g) * xstride + kbi * 64 + t * 16));
+                else b = bq[i][n];
+                mma_bf16_16816(acc[i & 1][n], r.x, s.x, r.y, s.y, b.x, b.y);
+                mma_bf16_16816(acc[i & 1][n], r.z, s.z, r.w, s.w, b.z, b.w);
+              }
+            }
+            if (++kbi == KB) {  // tile boundary inside the run: spill this tile's partial sums
+              flush_acc<NT>(acc, pp + seg * (NT * 8) * PCOL, nct, t, g);
+              kbi = 0;
+              ++seg;
+            }
+          }
+        }
+        __syncwarp();
+        ring_release(rg);
+        ring_produce(rg, meta, P, niter, warp, lane, pol_keep, pol_stream, cp_phases);
+        u += nb;
       }
-      ++seg;
-      u += nk;
+      if (kbi != 0) flush_acc<NT>(acc, pp + seg * (NT * 8) * PCOL, nct, t, g);
     }
     __syncthreads();
-    PROF_MARK(4);
-    // ---- cross-warp reduce + epilogue, one element per thread-iteration (independent global round trips)
-    const bool swiglu = epi == EPI_SWIGLU;
-    const int rsh = swiglu ? 3 : 4;  // rows per tile: 8 (gate/up pairs) or 16
-    const int nelem = (skip & 4) ? 0 : (TB << rsh) * nc;
+    PROF_MARK(3);
+    // ---- cross-warp reduce + epilogue, one output element per thread-iteration
 #pragma unroll 1
-    for (int e = tid; e < nelem; e += NTHREADS) {
+    for (int e = tid, it = 0; e < nelem; e += NTHREADS, ++it) {
       const int r = e & ((1 << rsh) - 1);
-      const int q = e >> rsh;
-      const int col = q / TB, tl = q - col * TB;
-      const int wf = (tl * KB) / upw, wl = ((tl + 1) * KB - 1) / upw;
-      const int tile = t0 + tb0 + tl;
+      const int tl = (e >> rsh) & ((1 << tbl) - 1);
+      const int col = e >> (rsh + tbl);
+      if (tl >= TB) continue;
+      const int tile = t0 + round * 8 + tl;
       const int row = tile * 16 + r;
-      float resid = 0.f;
-      if (epi == EPI_RESID) resid = bf2f(ldcg_bf16(reinterpret_cast<bf16*>(dst) + (size_t)col * dst_ld + row));  // in flight
+      float rs = 0.f;
+      if (epi == EPI_RESID) rs = it < 2 ? resid[it & 1] : bf2f(ldcg_bf16(reinterpret_cast<const bf16*>(dst) + (size_t)col * dst_ld + row));
       float s0 = 0.f, s1 = 0.f;
+      const int wf = tab->wf[tl], wl = tab->wl[tl];
 #pragma unroll 4
       for (int w = wf; w <= wl; ++w) {
-        const int sg = tl - (w * upw) / KB;
-        const float* pp = part + ((w * 2 + sg) * (NT * 8) + col) * PCOL;
-        s0 += pp[r];
-        if (swiglu) s1 += pp[r + 8];
+        const float* pq = part + ((w * 2 + (tl - tab->tl0[w])) * (NT * 8) + col) * PCOL;
+        s0 += pq[r];
+        if (swiglu) s1 += pq[r + 8];
       }
       if (swiglu) {
         // rows 0-7 = gate, 8-15 = up of the same 8 intermediate channels (:853-855, bf16 rounding points)
@@ -317,14 +464,14 @@ __device__ __noinline__ void gemv_phase(const Phase& ph, const KParams& P, unsig
       } else if (epi == EPI_LOGITS) {  // bf16 linear output, then .float() (HF _sample)
         reinterpret_cast<float*>(dst)[(size_t)col * dst_ld + row] = rbf(s0);
       } else {
-        if (epi == EPI_BIAS) s0 += bf2f(bias[row]);
-        else if (epi == EPI_RESID) s0 = resid + rbf(s0);
+        if (epi == EPI_BIAS) s0 += bf2f(ph.bias[row]);
+        else if (epi == EPI_RESID) s0 = rs + rbf(s0);
         reinterpret_cast<bf16*>(dst)[(size_t)col * dst_ld + row] = f2bf(s0);
       }
     }
-    __syncthreads();
-    PROF_MARK(5);
+    PROF_MARK(4);
   }
+  __syncthreads();
 }
 
 }  // namespace

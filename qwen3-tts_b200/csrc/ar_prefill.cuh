@@ -39,6 +39,24 @@ __global__ void pf_rmsnorm_kernel(const bf16* __restrict__ x, const bf16* __rest
   }
 }
 
+// packed-token index (row, position) of all prompt tokens, built on the device from the prompt lengths (passed by
+// value: no host staging buffer, no synchronisation), and the gather of every row's last hidden state
+struct PfLens { int B; int start[MAXB + 1]; };
+__global__ void pf_index_kernel(PfLens L, int* __restrict__ tok_seq, int* __restrict__ tok_pos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L.start[L.B]) return;
+  int b = 0;
+  while (i >= L.start[b + 1]) ++b;
+  tok_seq[i] = b;
+  tok_pos[i] = i - L.start[b];
+}
+__global__ void pf_gather_last_kernel(PfLens L, const bf16* __restrict__ x, bf16* __restrict__ h_last, int H) {
+  const int b = blockIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)(L.start[b + 1] - 1) * H);
+  uint4* dst = reinterpret_cast<uint4*>(h_last + (size_t)b * H);
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) dst[i] = src[i];
+}
+
 // per (token, head-vector): q heads RMSNorm+RoPE in place; k head -> K cache (normed, roped); v head -> V cache
 __global__ void pf_qkv_post_kernel(bf16* __restrict__ qkv, int ntok, const int* __restrict__ tok_seq, const int* __restrict__ tok_pos,
                                    int nh, int nkv, const bf16* __restrict__ qn, const bf16* __restrict__ kn, float eps,

@@ -13,17 +13,25 @@ constexpr int MAXCOLS = 32;      // columns per pass (batch rows or prefill toke
 constexpr int MAXSPLIT = 16;
 constexpr int RMAX = 2;          // max GQA group size (q heads per kv head)
 constexpr int PCOL = 20;         // padded row count of a partial column (bank-conflict-free)
-constexpr int XS_COL_BYTES = 4096 + 64;     // one staged column: K=2048 bf16 (+64 B skew)
-constexpr int XS_BYTES = 32 * XS_COL_BYTES;  // staged activations at NT=4: 32 cols
-// Shared memory is sized per batch class (NT n8-tiles): a small request leaves most of the 228 KB as L1, which is
-// what absorbs register spills / ABI stack traffic (with a 216 KB request every spill is an L2 round trip).
-constexpr int ATT_SMEM = (2 * 2 * 128 + 32 * 2 * 130) * 4;    // attention: qs (<= 2 queries) + per-half-warp partials
+// ---- shared-memory plan of the frame-step kernel (host-computed per launch class, see make_smem_plan) -------------
+//   [ x area | part | nw | weight rings | phase metas | mbarriers + round tables ]
+// x area : staged activations [cols][K] bf16 (rows skewed by 64 B), aliased by the attention / sampler phases
+// part   : split-K partial sums [warp][seg][col][PCOL] fp32
+// nw     : RMSNorm weights of the current GEMV phase (<= 2048 bf16)
+// rings  : per warp R slots of SB KB, filled by cp.async.bulk (TMA) ahead of the consumer, across phases
+constexpr int SMEM_OPTIN = 232448;             // 227 KB per CTA on sm_100
+constexpr int MAX_PHASES = 640;                // phases per program (meta table)
+constexpr int ATT_SMEM = (2 * 2 * 128 + 32 * 2 * 130) * 4 + 2 * 96 * 128 * 2;  // attention: fp32 queries + half-warp partials + 96-row K and V windows
 constexpr int SAMPLER_SMEM = (2 * 4096 + 64 + 256) * 4;
-__host__ __device__ constexpr int xs_bytes_nt(int nt) { return nt * 8 * XS_COL_BYTES; }
-__host__ __device__ constexpr int part_bytes_nt(int nt) { return 16 * 2 * nt * 8 * 20 * 4; }
-__host__ __device__ constexpr int smem_bytes_nt(int nt) {
-  return (xs_bytes_nt(nt) + part_bytes_nt(nt) > ATT_SMEM ? xs_bytes_nt(nt) + part_bytes_nt(nt) : ATT_SMEM) + 1024;
-}
+constexpr int X_MIN_BYTES = 83 * 1024;         // >= ATT_SMEM, SAMPLER_SMEM
+constexpr int NW_BYTES = 4096;
+constexpr int MAX_SLOTS = 8;
+__host__ __device__ constexpr int x_budget_nt(int nt) { return nt <= 2 ? 16 * (2 * 3072 + 64) : 32 * (2 * 2048 + 64); }
+__host__ __device__ constexpr int part_bytes_nt(int nt) { return NWARPS * 2 * nt * 8 * PCOL * 4; }
+
+struct SmemPlan {
+  int x_off, x_bytes, part_off, nw_off, ring_off, slot_blocks, nslots, meta_off, bar_off, total;
+};
 constexpr int MAXV = 4096;       // max vocab handled by the sampler
 
 enum PhaseType { PH_GEMV = 0, PH_ATTN = 1, PH_SAMPLE = 2 };
@@ -51,7 +59,7 @@ struct Phase {
   const bf16* kn;
   // ---- SAMPLE
   int group;           // 0 = talker codebook-0; j>=1 = code predictor codebook j
-  int pad_;
+  int staged;          // GEMV: activations are staged in the x area (else B fragments come straight from L2)
 };
 
 struct StackDev {
@@ -66,6 +74,7 @@ struct StackDev {
 
 struct DevState {
   unsigned int bar_count;
+  unsigned int bar_flags[256];   // flag barrier: one monotonically increasing epoch word per CTA (follows bar_count: one memset)
   int error;
   int B;
   int step;            // frames whose 16 codes are complete
@@ -111,7 +120,11 @@ struct KParams {
   int n_forced;
   float* dbg_tlogits;
   float* dbg_clogits;
-  int dbg_skip;             // ablation bits (tools/ablate_phase.py): 1 stage, 2 main loop, 4 epilogue, 8 preload, 16 whole body
+  int flags;                // A/B knobs (Q3_FLAGS): 1 counter barrier instead of flags, 2 LDG staging of un-normed inputs instead of TMA
+  SmemPlan plan;
+  float keep_fraction;      // share of the code predictor's weight lines fetched with L2 evict_last priority
+  int cp_phases;            // phases [0, cp_phases) of the frame program belong to the code predictor
+  const char* wbase;        // lowest address of the packed GEMV weights (PMeta offsets are relative to it)
   unsigned long long* prof;  // [n_phases][grid][8] globaltimer ns: [0] phase end, [1] barrier passed, [2..5] inner marks, [6] start
 };
 

@@ -158,12 +158,12 @@ __global__ void dwconv_ln_kernel(const bf16* __restrict__ x, const float* __rest
 }
 
 // final causal conv k=7, C -> 1, + clamp(-1,1) (…v2.py:863,884); one thread per output sample
-__global__ void final_conv_kernel(const bf16* __restrict__ x, const float* __restrict__ w /*[7][C]*/, float bias,
+__global__ void final_conv_kernel(const bf16* __restrict__ x, const float* __restrict__ w /*[7][C]*/, const float* __restrict__ bias_p,
                                   float* __restrict__ wav, int B, int T, int C) {
   const size_t total = (size_t)B * T;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int t = (int)(i % T);
-    float acc = bias;
+    float acc = __ldg(bias_p);
     for (int j = 0; j < 7; ++j) {
       const int tt = t - 6 + j;
       if (tt < 0) continue;
@@ -463,10 +463,7 @@ extern "C" int q3_codec_forward(q3_codec* c, const int32_t* codes_dev, int32_t B
     const float* w = R.f32("dec.out.w", (int64_t)7 * Cfin);
     const float* bsrc = R.f32("dec.out.b", 1);
     if (R.err) return 1;
-    float bias_h = 0.f;
-    Q3_CUDA(cudaMemcpyAsync(&bias_h, bsrc, sizeof(float), cudaMemcpyDeviceToHost, stream));
-    Q3_CUDA(cudaStreamSynchronize(stream));
-    final_conv_kernel<<<1184, 256, 0, stream>>>(act, w, bias_h, wav_dev, B, Tc, Cfin);
+    final_conv_kernel<<<1184, 256, 0, stream>>>(act, w, bsrc, wav_dev, B, Tc, Cfin);  // bias read on the device: no host round trip
     c->launches++;
   }
   Q3_CUDA(cudaGetLastError());

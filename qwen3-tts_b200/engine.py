@@ -189,13 +189,34 @@ class AREngine:
         return a.value, s.value
 
     # ------------------------------------------------------------------ seam B
+    def _frame_budget(self, inputs_embeds, sp: SamplingParams) -> int:
+        """Frames this request may generate: HF emits max_new_tokens-1 complete frames; the KV cache holds
+        max_ctx positions per row, so the horizon is clamped to max_ctx - longest prompt (the reference runs to EOS
+        under max_position_embeddings=32768; an engine built with a smaller max_ctx says so instead of failing
+        after the prefill).  Checked BEFORE any device work."""
+        H = self.cfg.talker.hidden_size
+        longest = max(int(e.reshape(-1, H).shape[0]) for e in inputs_embeds)
+        if longest >= self.max_ctx:
+            raise ValueError(f"prompt of {longest} positions does not fit max_ctx={self.max_ctx}")
+        want = max(int(sp.max_new_tokens) - 1, 0)
+        room = self.max_ctx - longest
+        if want > room:
+            if not getattr(self, "_warned_clamp", False):
+                import warnings
+                warnings.warn(f"max_new_tokens={sp.max_new_tokens} exceeds the KV capacity (max_ctx={self.max_ctx}, longest "
+                              f"prompt {longest}): generation is capped at {room} frames; build the engine with a larger "
+                              f"max_ctx to lift the cap", RuntimeWarning, stacklevel=3)
+                self._warned_clamp = True
+            want = room
+        return want
+
     @torch.no_grad()
     def generate(self, inputs_embeds, trailing_text, tts_pad_embed, sp: SamplingParams) -> List[torch.Tensor]:
         """Returns per-row LongTensor (N_i, G) trimmed at the first EOS (modeling_qwen3_tts.py:2283-2290).
         HF emits max_new_tokens-1 complete frames when no EOS is sampled."""
         B = len(inputs_embeds)
         G = self.cfg.num_code_groups
-        max_frames = max(int(sp.max_new_tokens) - 1, 0)
+        max_frames = self._frame_budget(inputs_embeds, sp)
         self.prefill(inputs_embeds, trailing_text, tts_pad_embed, sp)
         codes = torch.zeros(B, max(max_frames, 1), G, dtype=torch.int32, device=self.device)
         if max_frames > 0:
@@ -211,7 +232,7 @@ class AREngine:
         (n_i, G) code tensors per row (packet = 4 frames = 320 ms, Qwen3-TTS report §3.4)."""
         B = len(inputs_embeds)
         G = self.cfg.num_code_groups
-        max_frames = max(int(sp.max_new_tokens) - 1, 0)
+        max_frames = self._frame_budget(inputs_embeds, sp)
         self.prefill(inputs_embeds, trailing_text, tts_pad_embed, sp)
         codes = torch.zeros(B, max(max_frames, 1), G, dtype=torch.int32, device=self.device)
         emitted = [0] * B

@@ -11,6 +11,7 @@ Construction takes a state_dict + config + a `processor` callable (`processor(te
 ["input_ids"]`); `from_pretrained` (checkpoint.py) builds those from a HF checkpoint directory like the reference's.
 """
 from dataclasses import dataclass
+import dataclasses
 import os
 from typing import Any, Dict, List, Optional, Tuple, Union
 
@@ -200,13 +201,17 @@ class Qwen3TTSForConditionalGenerationB200:
                  speakers=None, non_streaming_mode=False, max_new_tokens: int = 4096, do_sample: bool = True,
                  top_k: int = 50, top_p: float = 1.0, temperature: float = 0.9, subtalker_dosample: bool = True,
                  subtalker_top_k: int = 50, subtalker_top_p: float = 1.0, subtalker_temperature: float = 0.9,
-                 eos_token_id: Optional[int] = None, repetition_penalty: float = 1.05, seed: int = 0, **kwargs):
+                 eos_token_id: Optional[int] = None, repetition_penalty: float = 1.05, seed: Optional[int] = None, **kwargs):
         """Signature and return of :2022-2043 / :2292.  The second return value (per-step hidden states) is not
         produced by the fused engine; the reference's own wrappers discard it."""
         embeds, trailing, pad = self.build_prefill(input_ids, instruct_ids, ref_ids, voice_clone_prompt, languages,
                                                    speakers, non_streaming_mode)
         if eos_token_id is not None and eos_token_id != self.cfg.codec_eos_token_id:
             raise ValueError("eos_token_id must equal config.talker_config.codec_eos_token_id in the fused engine")
+        if seed is None:
+            # the reference samples from torch's global RNG (torch.multinomial): repeated calls differ and
+            # torch.manual_seed() makes them reproducible — draw the Philox key from that same generator
+            seed = int(torch.randint(0, 2 ** 62, (), dtype=torch.int64).item())
         sp = SamplingParams(do_sample=do_sample, top_k=top_k, top_p=top_p, temperature=temperature,
                             repetition_penalty=repetition_penalty, subtalker_dosample=subtalker_dosample,
                             subtalker_top_k=subtalker_top_k, subtalker_top_p=subtalker_top_p,
@@ -216,7 +221,10 @@ class Qwen3TTSForConditionalGenerationB200:
         out: List[torch.Tensor] = []
         mb = self.engine.max_batch
         for s in range(0, len(embeds), mb):  # the reference runs one padded batch; we tile by engine capacity
-            out += self.engine.generate(embeds[s:s + mb], tr[s:s + mb], pad, sp)
+            # Philox streams are keyed (seed; row, frame, group) with the row index local to a tile: give every
+            # tile its own key so row b of two tiles never shares uniforms
+            sp_t = sp if s == 0 else dataclasses.replace(sp, seed=(sp.seed ^ (s * 0x9E3779B97F4A7C15)) & (2 ** 63 - 1))
+            out += self.engine.generate(embeds[s:s + mb], tr[s:s + mb], pad, sp_t)
         return out, [None] * len(out)
 
 
@@ -367,31 +375,41 @@ class Qwen3TTSTokenizer:
         """:259-365 — accepts an encode()-style output (has .audio_codes), a dict or a list of dicts whose
         "audio_codes" is a (T,K) tensor / ndarray; pads with -1, decodes, trims to T_i*1920, returns float32 numpy."""
         if hasattr(encoded, "audio_codes"):
-            codes_list = list(encoded.audio_codes)
+            codes_in = encoded.audio_codes
         elif isinstance(encoded, dict):
-            codes_list = [encoded["audio_codes"]] if "audio_codes" in encoded else None
+            if "audio_codes" not in encoded:
+                raise ValueError("`encoded` dict must contain 'audio_codes'.")
+            codes_in = encoded["audio_codes"]
         elif isinstance(encoded, list):
-            codes_list = [e["audio_codes"] for e in encoded]
+            codes_in = [e["audio_codes"] for e in encoded]
         else:
             raise TypeError("`encoded` must be an encode output, a dict, or a list of dicts.")
-        if codes_list is None:
-            raise ValueError("`encoded` dict must contain 'audio_codes'.")
-        tens = []
-        for c in codes_list:
-            if isinstance(c, np.ndarray):
-                c = torch.from_numpy(c)
-            if not isinstance(c, torch.Tensor):
-                raise TypeError("audio_codes must be a torch.Tensor or np.ndarray")
-            if c.dim() != 2:
-                raise ValueError(f"audio_codes must have shape (T, K), got {tuple(c.shape)}")
-            tens.append(c.to(self.device, torch.long))
-        Tm = max(int(c.shape[0]) for c in tens)
-        K = tens[0].shape[1]
-        ac = torch.full((len(tens), max(Tm, 1), K), -1, dtype=torch.long, device=self.device)
-        for i, c in enumerate(tens):
-            ac[i, :c.shape[0]] = c
-        wavs = self.decoder.decode(ac)
-        return [w.to(torch.float32).detach().cpu().numpy() for w in wavs], 24000
+        if isinstance(codes_in, torch.Tensor):
+            # :312-322 — a single (T, K) sample is unsqueezed, a 3-D tensor is an already padded (B, T, K) batch
+            t = codes_in
+            if t.dim() == 2:
+                t = t.unsqueeze(0)
+            if t.dim() != 3:
+                raise ValueError(f"audio_codes tensor must have shape (T, K) or (B, T, K), got {tuple(t.shape)}")
+            ac = t.to(self.device, torch.long)
+        else:
+            tens = []
+            for c in codes_in:  # :323-326 — list of per-sample tensors / arrays, right-padded with -1
+                c = c if isinstance(c, torch.Tensor) else torch.from_numpy(np.asarray(c))
+                if c.dim() != 2:
+                    raise ValueError(f"audio_codes must have shape (T, K), got {tuple(c.shape)}")
+                tens.append(c.to(self.device, torch.long))
+            if not tens:
+                return [], int(self.get_output_sample_rate())
+            Tm = max(int(c.shape[0]) for c in tens)
+            ac = torch.full((len(tens), max(Tm, 1), tens[0].shape[1]), -1, dtype=torch.long, device=self.device)
+            for i, c in enumerate(tens):
+                ac[i, :c.shape[0]] = c
+        wavs = []
+        mb = max(int(getattr(self.decoder, "max_batch", ac.shape[0])), 1)
+        for s0 in range(0, ac.shape[0], mb):  # tile by the codec engine's batch capacity (like model.generate)
+            wavs += self.decoder.decode(ac[s0:s0 + mb])
+        return [w.to(torch.float32).detach().cpu().numpy() for w in wavs], int(self.get_output_sample_rate())
 
 
 class Qwen3TTSModel:

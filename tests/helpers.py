@@ -140,3 +140,20 @@ def write_tiny_checkpoint(directory, device="cpu", sharded=False, seed=0, model_
     json.dump(tok, open(os.path.join(directory, "speech_tokenizer", "config.json"), "w"))
     save_file(sd, os.path.join(directory, "speech_tokenizer", "model.safetensors"))
     return cfg, W, ccfg, DW, ecfg, EW
+
+
+def report_parity(name, record):
+    """Parity figures the GPU tests measure (free-running exact-match rates, worst logit errors): printed, and
+    collected into gpurun_out/parity_report.json so a GPU run leaves them behind as an artifact."""
+    import json, os
+    print(f"[parity] {name}: {json.dumps(record)}")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        path = os.path.join(out, "parity_report.json")
+        data = json.load(open(path)) if os.path.exists(path) else {}
+        data[name] = record
+        json.dump(data, open(path, "w"), indent=1, sort_keys=True)
+    except OSError:
+        pass

@@ -57,12 +57,14 @@ def test_engine_fails_loudly_without_gpu():
 
 def test_sass_is_sm100a_with_tcgen05_tma():
     """The shipped cubins target sm_100a; the codec/prefill GEMM carries tcgen05 (UTCHMMA), TMEM loads (LDTM) and
-    TMA tile loads (UTMALDG); the decode kernel carries the bulk L2 prefetch (UBLKPF) and mma.sync (HMMA)."""
+    TMA tile loads (UTMALDG); the frame-step kernel stages its weights with bulk TMA copies into shared memory
+    (UBLKCP.S.G) completed on mbarriers (SYNCS...TRYWAIT), prefetches KV rows with cp.async (LDGSTS) and runs the
+    batch-in-N mma.sync (HMMA)."""
     import subprocess
     from qwen3_tts_b200 import build
     path = build.build()
     out = subprocess.run(["cuobjdump", "-lelf", path], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UBLKPF", "HMMA"):
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UBLKCP.S.G", "SYNCS.PHASECHK.TRANS64.TRYWAIT", "LDGSTS", "HMMA"):
         assert mnemonic in sass, f"{mnemonic} missing from SASS"
