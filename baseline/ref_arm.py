@@ -26,6 +26,28 @@ def reference_installed() -> bool:
     return os.path.isdir(os.path.join(REF_ROOT, "qwen_tts"))
 
 
+class _no_random_init:
+    """Skip torch's default random initialisation while the reference modules are constructed (2 G parameters of
+    kaiming/normal draws that load_state_dict overwrites anyway).  Touches torch.nn only, not the reference."""
+
+    def __enter__(self):
+        self.saved = []
+        for cls in (torch.nn.Linear, torch.nn.Embedding, torch.nn.Conv1d, torch.nn.ConvTranspose1d):
+            self.saved.append((cls, cls.reset_parameters))
+            cls.reset_parameters = lambda self_: None
+        self.init = {n: getattr(torch.nn.init, n) for n in ("normal_", "trunc_normal_", "kaiming_uniform_", "uniform_", "xavier_uniform_")}
+        for n in self.init:
+            setattr(torch.nn.init, n, lambda t, *a, **k: t)
+        return self
+
+    def __exit__(self, *exc):
+        for cls, fn in self.saved:
+            cls.reset_parameters = fn
+        for n, fn in self.init.items():
+            setattr(torch.nn.init, n, fn)
+        return False
+
+
 class ReferenceArm:
     def __init__(self, ocfg, occfg, W_f32, CW_f32, threads):
         torch.set_num_threads(threads)
@@ -37,9 +59,10 @@ class ReferenceArm:
                 os.environ["QWEN3TTS_REFERENCE_ROOT"] = REF_ROOT
                 from oracle import ref_shims, ref_driver as R
                 ref_shims.REFERENCE_ROOT = REF_ROOT
-                self.talker = R.build_reference_talker(ocfg)
+                with _no_random_init():  # every parameter is overwritten by the seeded synthetic weights below
+                    self.talker = R.build_reference_talker(ocfg)
+                    self.decoder = R.build_reference_codec_decoder(occfg)
                 R.load_weights_into_reference(self.talker, W_f32)
-                self.decoder = R.build_reference_codec_decoder(occfg)
                 self.decoder.load_state_dict(CW_f32, strict=False)
                 self.kind = "reference"
             except Exception as e:  # an import problem must not take the bench line down

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) q3_step_kernel(const __grid_const
   __shared__ RoundTab s_tab;
   DevState* st = P.st;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool use_counter = (P.flags & 1) != 0;
+  const bool use_counter = (P.flags & 1) == 0;
   unsigned int epoch = 0;  // host resets bar_count / bar_flags to 0 before every launch
   PMeta* meta = reinterpret_cast<PMeta*>(smem + P.plan.meta_off);
   const uint32_t bar0 = smem_addr(smem + P.plan.bar_off);       // [NWARPS][R] ring barriers, then the x barrier

@@ -12,9 +12,10 @@ using q3ring::RunGeom;
 
 // ------------------------------------------------------------------------------------------------
 // grid barrier.  Two interchangeable implementations (KParams.flags bit 0):
-//   flags  (default): every CTA owns one epoch word; arrive = st.release of the new epoch, wait = warp 0 polls all
-//                     gridDim words (5 coalesced lines) until none is behind.  No atomics, no single hot address.
-//   counter         : release-red on one counter + relaxed poll (round-1 barrier).
+//   counter (default): release-red on one counter + relaxed poll by thread 0 (arrive -> release ~1.0 us measured).
+//   flags            : every CTA owns one epoch word; arrive = st.release of the new epoch, wait = warp 0 polls all
+//                      gridDim words.  Measured SLOWER on B200 (arrive -> release 3-4 us: 148 pollers x 5 lines), kept
+//                      as an A/B knob only (profiles/r02_barrier_ab.txt).
 // Polls are RELAXED on purpose: ld.acquire.gpu compiles to LDG.STRONG + CCTL.IVALL (a full L1 invalidation per
 // poll iteration).  Correctness does not need it: every cross-CTA read in this kernel is an L2 access
 // (ld.global.cg / cp.async.cg / cp.async.bulk), the writers released at gpu scope before their arrival became
@@ -158,8 +159,11 @@ __device__ __forceinline__ void ring_produce(Ring& rg, const PMeta* meta, const 
     const uint32_t bytes = (uint32_t)nb << 10;
     mbar_expect_tx(bar, bytes);
     // phases [0, cp_phases) of the frame program are the code predictor: its 157 MB are re-read 15x per frame
-    bulk_g2s(rg.slots + (uint32_t)(rg.p_slot * rg.SB) * 1024u, P.wbase + q3ring::prod_piece_offset(rg.prod), bytes, bar,
-             rg.prod.pi < cp_phases ? pol_keep : pol_stream);
+    if (P.flags & 4)
+      bulk_g2s_plain(rg.slots + (uint32_t)(rg.p_slot * rg.SB) * 1024u, P.wbase + q3ring::prod_piece_offset(rg.prod), bytes, bar);
+    else
+      bulk_g2s(rg.slots + (uint32_t)(rg.p_slot * rg.SB) * 1024u, P.wbase + q3ring::prod_piece_offset(rg.prod), bytes, bar,
+               rg.prod.pi < cp_phases ? pol_keep : pol_stream);
   }
   rg.prod.u += nb;
   if (++rg.p_slot == rg.R) rg.p_slot = 0;
@@ -386,6 +390,7 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const
       for (int n = 0; n < NT; ++n)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[0][n][q] = acc[1][n][q] = 0.f;
+      long long wait_cycles = 0;
       int u = rgm.u0;
       int kbi = rgm.u0 - tl0 * KB;
       int seg = 0;
@@ -405,7 +410,10 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const
               bq[i][n] = (i < nb && n < nct && col < nc) ? ldcg16(src + (size_t)col * src_ld + kk * 32 + t * 8) : make_uint4(0, 0, 0, 0);
             }
         }
+        long long w0 = 0;
+        if (g_prof_row) w0 = clock64();
         mbar_wait(rg.bars + 8u * rg.c_slot, (uint32_t)rg.c_par, P.st);
+        if (g_prof_row && tid == 0) wait_cycles += clock64() - w0;
         const uint32_t sp = rg.slots + (uint32_t)(rg.c_slot * rg.SB) * 1024u + (uint32_t)lane * 16u;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -434,6 +442,10 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const
         u += nb;
       }
       if (kbi != 0) flush_acc<NT>(acc, pp + seg * (NT * 8) * PCOL, nct, t, g);
+      if (tid == 0 && g_prof_row) {  // [5]: cycles warp 0 waited for ring data, [7]: when it finished its run
+        g_prof_row[5] = (unsigned long long)wait_cycles;
+        PROF_MARK(7);
+      }
     }
     __syncthreads();
     PROF_MARK(3);

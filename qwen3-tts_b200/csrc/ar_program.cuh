@@ -120,7 +120,7 @@ struct KParams {
   int n_forced;
   float* dbg_tlogits;
   float* dbg_clogits;
-  int flags;                // A/B knobs (Q3_FLAGS): 1 counter barrier instead of flags, 2 LDG staging of un-normed inputs instead of TMA
+  int flags;                // A/B knobs (Q3_FLAGS): 1 flag barrier instead of the counter, 2 LDG staging of un-normed inputs instead of TMA, 4 weight copies without L2 policies
   SmemPlan plan;
   float keep_fraction;      // share of the code predictor's weight lines fetched with L2 evict_last priority
   int cp_phases;            // phases [0, cp_phases) of the frame program belong to the code predictor
