@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) q3_step_kernel(const __grid_const
       if (dhave) dreg = reinterpret_cast<const uint32_t*>(P.prog + nx)[tid];
       const Phase& ph = s_ph[slot];
       if (tid == 0) {
-        g_prof_row = (P.prof && it == 0) ? P.prof + ((size_t)pi * gridDim.x + blockIdx.x) * 8 : nullptr;
+        g_prof_row = (P.prof && it == 0) ? P.prof + ((size_t)pi * gridDim.x + blockIdx.x) * 16 : nullptr;
         PROF_MARK(6);
       }
       const int type = ph.type;

@@ -390,7 +390,8 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const
       for (int n = 0; n < NT; ++n)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[0][n][q] = acc[1][n][q] = 0.f;
-      long long wait_cycles = 0;
+      long long wait_cycles = 0, comp_cycles = 0, prod_cycles = 0;
+      PROF_MARK(8);
       int u = rgm.u0;
       int kbi = rgm.u0 - tl0 * KB;
       int seg = 0;
@@ -413,7 +414,8 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const
         long long w0 = 0;
         if (g_prof_row) w0 = clock64();
         mbar_wait(rg.bars + 8u * rg.c_slot, (uint32_t)rg.c_par, P.st);
-        if (g_prof_row && tid == 0) wait_cycles += clock64() - w0;
+        long long w1 = 0;
+        if (g_prof_row) { w1 = clock64(); if (tid == 0) wait_cycles += w1 - w0; }
         const uint32_t sp = rg.slots + (uint32_t)(rg.c_slot * rg.SB) * 1024u + (uint32_t)lane * 16u;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -438,12 +440,21 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const
         }
         __syncwarp();
         ring_release(rg);
-        ring_produce(rg, meta, P, niter, warp, lane, pol_keep, pol_stream, cp_phases);
+        long long p0 = 0;
+        if (g_prof_row) p0 = clock64();
+        if (!(P.flags & 8) || rg.outstanding == 0) ring_produce(rg, meta, P, niter, warp, lane, pol_keep, pol_stream, cp_phases);
+        if (g_prof_row && tid == 0) { prod_cycles += clock64() - p0; comp_cycles += p0 - w1; }
         u += nb;
       }
       if (kbi != 0) flush_acc<NT>(acc, pp + seg * (NT * 8) * PCOL, nct, t, g);
-      if (tid == 0 && g_prof_row) {  // [5]: cycles warp 0 waited for ring data, [7]: when it finished its run
+      if (P.flags & 8) {
+#pragma unroll 1
+        for (int i = 0; i < rg.R; ++i) ring_produce(rg, meta, P, niter, warp, lane, pol_keep, pol_stream, cp_phases);
+      }
+      if (tid == 0 && g_prof_row) {  // warp 0: [5] cycles waiting for ring data, [9] computing, [10] in ring_produce; [7] run finished
         g_prof_row[5] = (unsigned long long)wait_cycles;
+        g_prof_row[9] = (unsigned long long)comp_cycles;
+        g_prof_row[10] = (unsigned long long)prod_cycles;
         PROF_MARK(7);
       }
     }

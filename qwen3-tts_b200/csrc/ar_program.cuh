@@ -120,12 +120,12 @@ struct KParams {
   int n_forced;
   float* dbg_tlogits;
   float* dbg_clogits;
-  int flags;                // A/B knobs (Q3_FLAGS): 1 flag barrier instead of the counter, 2 LDG staging of un-normed inputs instead of TMA, 4 weight copies without L2 policies
+  int flags;                // A/B knobs (Q3_FLAGS): 1 flag barrier instead of the counter, 2 LDG staging of un-normed inputs instead of TMA, 4 weight copies without L2 policies, 8 ring refills after the main loop instead of inside it
   SmemPlan plan;
   float keep_fraction;      // share of the code predictor's weight lines fetched with L2 evict_last priority
   int cp_phases;            // phases [0, cp_phases) of the frame program belong to the code predictor
   const char* wbase;        // lowest address of the packed GEMV weights (PMeta offsets are relative to it)
-  unsigned long long* prof;  // [n_phases][grid][8] globaltimer ns: [0] phase end, [1] barrier passed, [2..5] inner marks, [6] start
+  unsigned long long* prof;  // [n_phases][grid][16]: globaltimer ns [0] phase end, [1] barrier passed, [2..4] inner marks, [6] start, [7],[8] warp-0 marks; cycles [5],[9],[10]
 };
 
 }  // namespace

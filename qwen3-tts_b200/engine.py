@@ -174,13 +174,13 @@ class AREngine:
         kinds = (C.c_int32 * n)()
         self.lib.q3_describe_frame_program(self.h, kinds, n)
         G = torch.cuda.get_device_properties(self.device).multi_processor_count
-        buf = torch.zeros(n, G, 8, dtype=torch.int64, device=self.device)
+        buf = torch.zeros(n, G, 16, dtype=torch.int64, device=self.device)
         _lib.check(self.lib.q3_set_profile(self.h, buf.data_ptr()))
         self.decode(max_frames, codes)
         torch.cuda.current_stream(self.device).synchronize()
         _lib.check(self.lib.q3_set_profile(self.h, None))
         t = buf.cpu().numpy()
-        self.last_profile_all = t  # [phase][cta][8]: 0 end, 1 barrier passed, 2..5 inner marks, 6 start
+        self.last_profile_all = t  # [phase][cta][16]: 0 end, 1 barrier passed, 2..4 inner marks, 6 start, 7/8 warp-0 marks, 5/9/10 cycle counts
         return list(kinds), t[:, 0, 0], t[:, 0, 1], t[:, 0, 2:6]
 
     def algorithmic_bytes(self, B, S):

@@ -26,12 +26,13 @@ for i, k in enumerate(kinds):
     last = int(np.argmax(end))
     d = agg.setdefault(key, [])
     m = T[i, last, 2:6]
-    d.append(dict(wait=T[i, last, 5] * 1e3 / 1965.0, w0done=(T[i, last, 7] - m[0]) if (T[i, last, 7] > 0 and m[0] > 0) else 0.0,
+    cyc = lambda j: T[i, last, j] * 1e3 / 1965.0
+    d.append(dict(wait=cyc(5), comp=cyc(9), prod=cyc(10), pre=(T[i, last, 8] - m[0]) if (T[i, last, 8] > 0 and m[0] > 0) else 0.0, w0done=(T[i, last, 7] - m[0]) if (T[i, last, 7] > 0 and m[0] > 0) else 0.0,
                   phase=end.max() - rel_prev.min(), skew_release=rel_prev.max() - rel_prev.min(),
                   body_last=end[last] - rel_prev[last], body_med=np.median(end - rel_prev), body_min=(end - rel_prev).min(),
                   arrive_to_release=passed.min() - end.max(), release_spread=passed.max() - passed.min(),
                   seg=[(m[0] - rel_prev[last]) if m[0] > 0 else 0, (m[1] - m[0]) if m[1] > 0 else 0, (m[2] - m[1]) if m[2] > 0 else 0,
-                       (m[3] - m[2]) if m[3] > 0 else 0, (end[last] - max(m.max(), rel_prev[last]))]))
+                       0.0, (end[last] - max(m[:3].max(), rel_prev[last]))]))
 print(f"B={a.batch} ctx={a.ctx}: all-CTA view; times in us (mean over phases of the kind)")
 print(f"{'kind':28s} {'n':>4s} {'phase':>6s} {'body_last':>9s} {'body_med':>8s} {'body_min':>8s} {'arr->rel':>8s} {'rel_spread':>10s} | last CTA segments: entry+stage loop epi (unused) exit")
 tot = 0
@@ -39,6 +40,6 @@ for k, v in agg.items():
     f = lambda n: np.mean([x[n] for x in v])
     seg = np.mean([x["seg"] for x in v], axis=0)
     tot += f("phase") * len(v)
-    print(f"[ring wait {f('wait'):5.2f} w0 run done +{f('w0done'):5.2f}] ", end="")
+    print(f"[w0: pre-loop {f('pre'):5.2f} wait {f('wait'):5.2f} compute {f('comp'):5.2f} produce {f('prod'):5.2f} run done +{f('w0done'):5.2f}] ", end="")
     print(f"{k:28s} {len(v):4d} {f('phase'):6.2f} {f('body_last'):9.2f} {f('body_med'):8.2f} {f('body_min'):8.2f} {f('arrive_to_release'):8.2f} {f('release_spread'):10.2f} | " + " ".join(f"{x:5.2f}" for x in seg))
 print(f"sum of phase times {tot:.0f} us")
