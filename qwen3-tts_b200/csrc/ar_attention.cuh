@@ -125,7 +125,7 @@ __device__ __noinline__ void attn_phase(const Phase& ph, const KParams& P, unsig
 #pragma unroll 1
   for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
     if (unit != (int)blockIdx.x) {  // later units of this CTA (B*nkv*nsplit > grid): fetch their window now
-      __syncthreads();
+      cta_sync();
       attn_window_issue(ph, P, smem, frame, unit);
     }
     const AttnUnit U = attn_unit(ph, P, S, frame, nsplit, unit);
@@ -164,7 +164,7 @@ __device__ __noinline__ void attn_phase(const Phase& ph, const KParams& P, unsig
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __threadfence_block();
-    __syncthreads();
+    cta_sync();
     PROF_MARK(2);
 
     const float scale = rsqrtf((float)HD);
@@ -240,7 +240,7 @@ __device__ __noinline__ void attn_phase(const Phase& ph, const KParams& P, unsig
       }
       // ---- combine the 32 half-warps
       PROF_MARK(3);
-      __syncthreads();
+      cta_sync();
 #pragma unroll
       for (int r = 0; r < RMAX; ++r) {
         if (r < R) {
@@ -250,7 +250,7 @@ __device__ __noinline__ void attn_phase(const Phase& ph, const KParams& P, unsig
           for (int i = 0; i < 8; ++i) rr[2 + l16 * 8 + i] = o[r][i];
         }
       }
-      __syncthreads();
+      cta_sync();
       float M = -INFINITY, L = 0.f, O = 0.f;
       // token t of this split maps to half-warp ((t>>2)<<1) | (t&1): only the first nhw half-warps hold data
       const int ntok = max(e1 - s0, 0);
@@ -279,9 +279,9 @@ __device__ __noinline__ void attn_phase(const Phase& ph, const KParams& P, unsig
           sb[rr_ * 130 + 2 + dd] = O;
         }
         __threadfence();
-        __syncthreads();
+        cta_sync();
         if (tid == 0) s_ticket = (int)atomicAdd(&P.st->split_cnt[seq * nkv + kvh], 1u);
-        __syncthreads();
+        cta_sync();
         if (s_ticket == nsplit - 1) {
           __threadfence();
           if (rr_ < R) {
@@ -301,7 +301,7 @@ __device__ __noinline__ void attn_phase(const Phase& ph, const KParams& P, unsig
           if (tid == 0) P.st->split_cnt[seq * nkv + kvh] = 0;
         }
       }
-      __syncthreads();
+      cta_sync();
     }
   }
 }

@@ -51,23 +51,28 @@ namespace {
 // the persistent kernel
 // ------------------------------------------------------------------------------------------------
 template <int NT>
-__global__ void __launch_bounds__(NTHREADS, 1) q3_step_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(CTA_THREADS, 1) q3_step_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ Phase s_ph[2];
   __shared__ RoundTab s_tab;
+  __shared__ int s_stop;
+  __shared__ int s_issued[NWARPS];
   DevState* st = P.st;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool use_counter = (P.flags & 1) == 0;
   unsigned int epoch = 0;  // host resets bar_count / bar_flags to 0 before every launch
   PMeta* meta = reinterpret_cast<PMeta*>(smem + P.plan.meta_off);
-  const uint32_t bar0 = smem_addr(smem + P.plan.bar_off);       // [NWARPS][R] ring barriers, then the x barrier
-  const uint32_t xbar = bar0 + 8u * (NWARPS * P.plan.nslots);
+  const int R = P.plan.nslots, SB = P.plan.slot_blocks;
+  const uint32_t full0 = smem_addr(smem + P.plan.bar_off);      // [NWARPS][R] full, [NWARPS][R] empty, then the x barrier
+  const uint32_t empty0 = full0 + 8u * (NWARPS * R);
+  const uint32_t xbar = empty0 + 8u * (NWARPS * R);
+  const uint32_t ring0 = smem_addr(smem + P.plan.ring_off);
   uint32_t xpar = 0;
   const int niter = P.mode == 1 ? P.max_iters : 1;
 
   // ---- per-CTA phase metas: which contiguous weight bytes this CTA consumes in every phase
 #pragma unroll 1
-  for (int i = tid; i < P.n_phases; i += NTHREADS) {
+  for (int i = tid; i < P.n_phases; i += CTA_THREADS) {
     const Phase* gp = P.prog + i;
     PMeta m;
     m.woff16 = 0; m.ntc = 0; m.kb = 0;
@@ -81,98 +86,109 @@ __global__ void __launch_bounds__(NTHREADS, 1) q3_step_kernel(const __grid_const
     meta[i] = m;
   }
   if (tid == 0) {
-    for (int i = 0; i < NWARPS * P.plan.nslots + 1; ++i) mbar_init(bar0 + 8u * i, 1);
+    for (int i = 0; i < 2 * NWARPS * R + 1; ++i) mbar_init(full0 + 8u * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");
     g_prof_row = nullptr;
+    s_stop = 0;
   }
+  if (tid < NWARPS) s_issued[tid] = -1;
   if (tid < (int)(sizeof(Phase) / 4))
     reinterpret_cast<uint32_t*>(&s_ph[0])[tid] = reinterpret_cast<const uint32_t*>(P.prog)[tid];
   __syncthreads();
-  if (s_ph[0].type == PH_GEMV && s_ph[0].norm_w != nullptr && tid < s_ph[0].kb * 4)
-    reinterpret_cast<uint4*>(smem + P.plan.nw_off)[tid] = reinterpret_cast<const uint4*>(s_ph[0].norm_w)[tid];
-  if (s_ph[0].type == PH_ATTN) attn_prefetch(s_ph[0], P, smem + P.plan.x_off, st->step);  // (synthetic profiling programs only)
 
-  // L2 eviction priorities of the weight stream (createpolicy): the code predictor's layer weights are re-read on
-  // every one of its 15 passes -> keep a fraction that fits beside the talker stream; everything else streams
-  uint64_t pol_keep, pol_stream;
-  asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol_keep) : "f"(P.keep_fraction));
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-  const int cp_phases = P.mode == 1 ? P.cp_phases : 0;
+  if (warp >= NWARPS) {
+    // ================= producer warp: the TMA weight stream of all eight consumer rings =================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+    if (warp == NWARPS) producer_loop(P, meta, niter, ring0, full0, empty0, &s_stop, s_issued, P.mode == 1 ? P.cp_phases : 0);
+  } else {
+    // ================= 8 consumer warps: the phase program =================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
+    if (s_ph[0].type == PH_GEMV && s_ph[0].norm_w != nullptr && tid < s_ph[0].kb * 4)
+      reinterpret_cast<uint4*>(smem + P.plan.nw_off)[tid] = reinterpret_cast<const uint4*>(s_ph[0].norm_w)[tid];
+    if (s_ph[0].type == PH_ATTN) attn_prefetch(s_ph[0], P, smem + P.plan.x_off, st->step);  // (synthetic profiling programs only)
+    Ring rg;
+    rg.SB = SB; rg.R = R;
+    rg.slots = ring0 + (uint32_t)(warp * R * SB) * 1024u;
+    rg.full = full0 + 8u * (warp * R);
+    rg.empty = empty0 + 8u * (warp * R);
+    rg.c_slot = 0; rg.c_par = 0; rg.consumed = 0;
+    cta_sync();
 
-  // ---- weight ring of this warp: start streaming before anything else happens
-  Ring rg;
-  q3ring::prod_init(rg.prod);
-  rg.SB = P.plan.slot_blocks; rg.R = P.plan.nslots;
-  rg.slots = smem_addr(smem + P.plan.ring_off) + (uint32_t)(warp * rg.R * rg.SB) * 1024u;
-  rg.bars = bar0 + 8u * (warp * rg.R);
-  rg.c_slot = 0; rg.c_par = 0; rg.p_slot = 0; rg.outstanding = 0;
-  q3ring::prod_next_run(rg.prod, meta, P.n_phases, niter, warp);
+    const int step_base = st->step;
+    int iters_done = 0;
+    int slot = 0;
 #pragma unroll 1
-  for (int i = 0; i < rg.R; ++i) ring_produce(rg, meta, P, niter, warp, lane, pol_keep, pol_stream, cp_phases);
-  __syncthreads();
-
-  const int step_base = st->step;
-  int iters_done = 0;
-  int slot = 0;
-#pragma unroll 1
-  for (int it = 0; it < niter; ++it) {
-    const int frame = step_base + it;
-    if (P.mode == 1) {
-      bool all = true;
-      for (int b = 0; b < P.B; ++b) all = all && (ldcgi(&st->finished[b]) != 0);
-      if (all) break;
-    }
-#pragma unroll 1
-    for (int pi = 0; pi < P.n_phases; ++pi) {
-      // descriptor of this phase sits in s_ph[slot] (fetched one phase ahead).  The load of the NEXT descriptor is
-      // issued now into a register and only stored to smem after the body, so its L2 round trip is hidden.
-      int nx = pi + 1;
-      if (nx >= P.n_phases) nx = (P.mode == 1) ? 0 : -1;
-      const bool dhave = nx >= 0 && tid < (int)(sizeof(Phase) / 4);
-      uint32_t dreg = 0;
-      if (dhave) dreg = reinterpret_cast<const uint32_t*>(P.prog + nx)[tid];
-      const Phase& ph = s_ph[slot];
-      if (tid == 0) {
-        g_prof_row = (P.prof && it == 0) ? P.prof + ((size_t)pi * gridDim.x + blockIdx.x) * 16 : nullptr;
-        PROF_MARK(6);
+    for (int it = 0; it < niter; ++it) {
+      const int frame = step_base + it;
+      if (P.mode == 1) {
+        bool all = true;
+        for (int b = 0; b < P.B; ++b) all = all && (ldcgi(&st->finished[b]) != 0);
+        if (all) break;
       }
-      const int type = ph.type;
-      if (type == PH_GEMV) gemv_phase<NT>(ph, meta[pi], P, rg, meta, niter, smem, &s_tab, xbar, xpar, pol_keep, pol_stream, cp_phases);
-      else if (type == PH_ATTN) attn_phase(ph, P, smem + P.plan.x_off, frame);
-      else sample_phase(ph, P, smem + P.plan.x_off, frame, P.mode == 0);
-      if (dhave) reinterpret_cast<uint32_t*>(&s_ph[slot ^ 1])[tid] = dreg;
-      __syncthreads();  // body done (global writes of every thread precede thread 0's release), next descriptor visible
-      PROF_MARK(0);
-      grid_arrive(st, epoch, use_counter);
-      // work that does not depend on the other CTAs, between arrive and wait: the next GEMV's RMSNorm weights
-      // (load now, store after the wait) and the KV rows the next attention phase will need
-      uint4 nwv = make_uint4(0, 0, 0, 0);
-      bool nw_have = false;
-      if (nx >= 0) {
-        const Phase& nph = s_ph[slot ^ 1];
-        if (nph.type == PH_GEMV && nph.norm_w != nullptr && tid < nph.kb * 4) {
-          nwv = reinterpret_cast<const uint4*>(nph.norm_w)[tid];
-          nw_have = true;
-        } else if (nph.type == PH_ATTN) {
-          attn_prefetch(nph, P, smem + P.plan.x_off, pi + 1 >= P.n_phases ? frame + 1 : frame);
+#pragma unroll 1
+      for (int pi = 0; pi < P.n_phases; ++pi) {
+        // descriptor of this phase sits in s_ph[slot] (fetched one phase ahead).  The load of the NEXT descriptor is
+        // issued now into a register and only stored to smem after the body, so its L2 round trip is hidden.
+        int nx = pi + 1;
+        if (nx >= P.n_phases) nx = (P.mode == 1) ? 0 : -1;
+        const bool dhave = nx >= 0 && tid < (int)(sizeof(Phase) / 4);
+        uint32_t dreg = 0;
+        if (dhave) dreg = reinterpret_cast<const uint32_t*>(P.prog + nx)[tid];
+        const Phase& ph = s_ph[slot];
+        if (tid == 0) {
+          g_prof_row = (P.prof && it == 0) ? P.prof + ((size_t)pi * gridDim.x + blockIdx.x) * 16 : nullptr;
+          PROF_MARK(6);
         }
+        const int type = ph.type;
+        if (type == PH_GEMV) gemv_phase<NT>(ph, meta[pi], P, rg, smem, &s_tab, xbar, xpar);
+        else if (type == PH_ATTN) attn_phase(ph, P, smem + P.plan.x_off, frame);
+        else sample_phase(ph, P, smem + P.plan.x_off, frame, P.mode == 0);
+        if (dhave) reinterpret_cast<uint32_t*>(&s_ph[slot ^ 1])[tid] = dreg;
+        cta_sync();  // body done (global writes of every thread precede thread 0's release), next descriptor visible
+        PROF_MARK(0);
+        grid_arrive(st, epoch, use_counter);
+        // work that does not depend on the other CTAs, between arrive and wait: the next GEMV's RMSNorm weights
+        // (load now, store after the wait) and the KV rows the next attention phase will need
+        uint4 nwv = make_uint4(0, 0, 0, 0);
+        bool nw_have = false;
+        if (nx >= 0) {
+          const Phase& nph = s_ph[slot ^ 1];
+          if (nph.type == PH_GEMV && nph.norm_w != nullptr && tid < nph.kb * 4) {
+            nwv = reinterpret_cast<const uint4*>(nph.norm_w)[tid];
+            nw_have = true;
+          } else if (nph.type == PH_ATTN) {
+            attn_prefetch(nph, P, smem + P.plan.x_off, pi + 1 >= P.n_phases ? frame + 1 : frame);
+          }
+        }
+        grid_wait(st, epoch, use_counter);
+        slot ^= 1;
+        if (nw_have) reinterpret_cast<uint4*>(smem + P.plan.nw_off)[tid] = nwv;
+        cta_sync();
+        PROF_MARK(1);
       }
-      grid_wait(st, epoch, use_counter);
-      slot ^= 1;
-      if (nw_have) reinterpret_cast<uint4*>(smem + P.plan.nw_off)[tid] = nwv;
-      __syncthreads();
-      PROF_MARK(1);
+      ++iters_done;
     }
-    ++iters_done;
-  }
-  // never leave with bulk copies in flight into this CTA's shared memory
+    // ---- shutdown: stop the producer, then drain what it had already requested (never leave with bulk copies in
+    // flight into this CTA's shared memory)
+    if (tid == 0) s_stop = 1;
+    cta_sync();
+    {
+      volatile int* vi = s_issued;
+      const long long t0 = clock64();
+      int issued;
+      while ((issued = vi[warp]) < 0) {
+        if (clock64() - t0 > 8000000000LL) { st->error = 80; __threadfence(); __trap(); }
+      }
 #pragma unroll 1
-  while (rg.outstanding > 0) {
-    mbar_wait(rg.bars + 8u * rg.c_slot, (uint32_t)rg.c_par, st);
-    ring_release(rg);
+      while (rg.consumed < issued) {
+        mbar_wait(rg.full + 8u * rg.c_slot, (uint32_t)rg.c_par, st);
+        ring_release(rg, lane);
+      }
+    }
+    if (P.mode == 1 && blockIdx.x == 0 && tid == 0) st->step = step_base + iters_done;
   }
-  if (P.mode == 1 && blockIdx.x == 0 && tid == 0) st->step = step_base + iters_done;
+  __syncthreads();
 }
 
 }  // namespace
@@ -446,7 +462,7 @@ static int make_smem_plan(q3_engine* e, std::vector<Phase>& prog, int B, int nt,
   pl.nw_off = pl.part_off + part_bytes_nt(nt);
   pl.ring_off = up(pl.nw_off + NW_BYTES, 1024);
   const int meta_bytes = up((int)prog.size() * (int)sizeof(q3ring::PMeta), 16);
-  const int bar_bytes = 8 * (NWARPS * MAX_SLOTS + 1) + 8;
+  const int bar_bytes = 8 * (2 * NWARPS * MAX_SLOTS + 1) + 8;  // full + empty barrier per ring slot, the x barrier
   const int avail = e->max_dyn_smem - pl.ring_off - meta_bytes - bar_bytes;
   pl.slot_blocks = 0;
   for (int sb : {4, 2, 1}) {
@@ -664,7 +680,7 @@ static int launch_program(q3_engine* e, int off, int n, int mode, int max_iters,
   void* args[] = {&P};
   const void* fn = nt == 1 ? (const void*)q3_step_kernel<1> : nt == 2 ? (const void*)q3_step_kernel<2>
                                                                      : (const void*)q3_step_kernel<4>;
-  Q3_CUDA(cudaLaunchCooperativeKernel(fn, dim3(e->sm_count), dim3(NTHREADS), args, (size_t)plan.total, stream));
+  Q3_CUDA(cudaLaunchCooperativeKernel(fn, dim3(e->sm_count), dim3(CTA_THREADS), args, (size_t)plan.total, stream));
   return 0;
 }
 

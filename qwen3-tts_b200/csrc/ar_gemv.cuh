@@ -28,7 +28,7 @@ __device__ __forceinline__ void barrier_timeout(DevState* st) {
 }
 
 __device__ __forceinline__ void grid_arrive(DevState* st, unsigned int& epoch, bool use_counter) {
-  // caller: __syncthreads() already executed (every thread's global writes happen-before thread 0's release)
+  // caller: cta_sync() already executed (every thread's global writes happen-before thread 0's release)
   if (threadIdx.x == 0) {
     if (use_counter) {
       epoch += gridDim.x;
@@ -69,6 +69,9 @@ __device__ __forceinline__ void grid_wait(DevState* st, unsigned int epoch, bool
     }
   }
 }
+
+// barrier of the 256 worker threads (named barrier 1): the producer warp never takes part in phase-level syncs
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // fine-grained profiling marks (thread 0 only, first frame of a profiled launch)
 __shared__ unsigned long long* g_prof_row;
@@ -134,46 +137,65 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-warp weight ring: the warp's lane 0 is the producer (cp.async.bulk into the warp's private slots), the whole
-// warp is the consumer.  Producer and consumer walk the same deterministic piece sequence (ar_ring.cuh); the
-// producer stays up to R pieces ahead, across phases and grid barriers, so weight streaming never waits for the
-// dependency chain of the activations.
+// weight rings.  Every consumer warp owns a private ring of R slots (SB KB each) in shared memory; ONE producer
+// warp feeds all eight: its lane w walks consumer warp w's deterministic piece sequence (ar_ring.cuh) and issues
+// one cp.async.bulk per piece as soon as the slot is free (empty mbarrier, armed by the consumer) — across phases
+// and grid barriers, so weight streaming never waits for the activations' dependency chain and none of the
+// producer's address arithmetic sits on the consumers' critical path (measured: ~0.3 us per piece when the consumer
+// warps produced for themselves, profiles/r02_phase_breakdown.txt).
 // ------------------------------------------------------------------------------------------------
-struct Ring {
-  ProdIter prod;
-  uint32_t slots;      // shared address of this warp's first slot
-  uint32_t bars;       // shared address of this warp's first full-barrier
-  int SB, R;           // blocks per slot, slots
-  int c_slot, c_par;   // consumer position / parity of the current lap
-  int p_slot;          // producer position
-  int outstanding;     // pieces requested and not yet consumed
+struct Ring {              // consumer-side view of one warp's ring
+  uint32_t slots;          // shared address of the warp's first slot
+  uint32_t full, empty;    // shared addresses of its first full / empty mbarrier
+  int SB, R;               // blocks per slot, slots
+  int c_slot, c_par;       // position / parity of the current lap
+  int consumed;            // pieces consumed so far
 };
 
-// one piece, if the ring has a free slot and the program has more work for this warp
-__device__ __forceinline__ void ring_produce(Ring& rg, const PMeta* meta, const KParams& P, int niter, int warp, int lane,
-                                             uint64_t pol_keep, uint64_t pol_stream, int cp_phases) {
-  if (rg.prod.done || rg.outstanding >= rg.R) return;
-  const int nb = q3ring::imin(rg.SB, rg.prod.u1 - rg.prod.u);
-  if (lane == 0) {
-    const uint32_t bar = rg.bars + 8u * rg.p_slot;
-    const uint32_t bytes = (uint32_t)nb << 10;
-    mbar_expect_tx(bar, bytes);
-    // phases [0, cp_phases) of the frame program are the code predictor: its 157 MB are re-read 15x per frame
-    if (P.flags & 4)
-      bulk_g2s_plain(rg.slots + (uint32_t)(rg.p_slot * rg.SB) * 1024u, P.wbase + q3ring::prod_piece_offset(rg.prod), bytes, bar);
-    else
-      bulk_g2s(rg.slots + (uint32_t)(rg.p_slot * rg.SB) * 1024u, P.wbase + q3ring::prod_piece_offset(rg.prod), bytes, bar,
-               rg.prod.pi < cp_phases ? pol_keep : pol_stream);
-  }
-  rg.prod.u += nb;
-  if (++rg.p_slot == rg.R) rg.p_slot = 0;
-  ++rg.outstanding;
-  if (rg.prod.u >= rg.prod.u1) q3ring::prod_next_run(rg.prod, meta, P.n_phases, niter, warp);
+__device__ __forceinline__ void ring_release(Ring& rg, int lane) {
+  __syncwarp();
+  if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rg.empty + 8u * rg.c_slot) : "memory");
+  if (++rg.c_slot == rg.R) { rg.c_slot = 0; rg.c_par ^= 1; }
+  ++rg.consumed;
 }
 
-__device__ __forceinline__ void ring_release(Ring& rg) {
-  if (++rg.c_slot == rg.R) { rg.c_slot = 0; rg.c_par ^= 1; }
-  --rg.outstanding;
+// the producer warp: lane w < NWARPS serves consumer warp w until its sequence ends or the workers say stop
+__device__ __forceinline__ void producer_loop(const KParams& P, const PMeta* meta, int niter, uint32_t ring0, uint32_t full0,
+                                              uint32_t empty0, volatile int* s_stop, volatile int* s_issued, int cp_phases) {
+  const int w = threadIdx.x & 31;
+  if (w >= NWARPS) return;
+  const int SB = P.plan.slot_blocks, R = P.plan.nslots;
+  uint64_t pol_keep, pol_stream;
+  asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol_keep) : "f"(P.keep_fraction));
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  ProdIter it;
+  q3ring::prod_init(it);
+  q3ring::prod_next_run(it, meta, P.n_phases, niter, w);
+  const uint32_t slots = ring0 + (uint32_t)(w * R * SB) * 1024u, full = full0 + 8u * (w * R), empty = empty0 + 8u * (w * R);
+  int slot = 0, par = 1;  // a fresh mbarrier passes a wait on the "previous" phase: the first lap never blocks
+  int issued = 0;
+  bool stop = false;
+  while (!it.done && !stop) {
+    const long long t0 = clock64();
+    while (!mbar_try(empty + 8u * slot, (uint32_t)par)) {
+      if (*s_stop) { stop = true; break; }
+      if (clock64() - t0 > 16000000000LL) { P.st->error = 79; __threadfence(); __trap(); }
+    }
+    if (stop) break;
+    const int nb = q3ring::imin(SB, it.u1 - it.u);
+    const uint32_t bytes = (uint32_t)nb << 10;
+    const uint32_t bar = full + 8u * slot;
+    mbar_expect_tx(bar, bytes);
+    // phases [0, cp_phases) of the frame program are the code predictor: its layer weights are re-read 15x per frame
+    if (P.flags & 4) bulk_g2s_plain(slots + (uint32_t)(slot * SB) * 1024u, P.wbase + q3ring::prod_piece_offset(it), bytes, bar);
+    else bulk_g2s(slots + (uint32_t)(slot * SB) * 1024u, P.wbase + q3ring::prod_piece_offset(it), bytes, bar,
+                  it.pi < cp_phases ? pol_keep : pol_stream);
+    it.u += nb;
+    if (it.u >= it.u1) q3ring::prod_next_run(it, meta, P.n_phases, niter, w);
+    if (++slot == R) { slot = 0; par ^= 1; }
+    ++issued;
+  }
+  s_issued[w] = issued;  // the consumer drains [consumed, issued) before the CTA exits
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -181,9 +203,9 @@ __device__ __forceinline__ void ring_release(Ring& rg) {
 // ------------------------------------------------------------------------------------------------
 __device__ __noinline__ float block_reduce(float v, float* red, int op /*0 max, 1 sum*/) {
   if (op == 0) v = warp_max(v); else v = warp_sum(v);
-  __syncthreads();
+  cta_sync();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
+  cta_sync();
   float r = red[threadIdx.x & (NWARPS - 1)];
 #pragma unroll
   for (int o = NWARPS / 2; o > 0; o >>= 1) {
@@ -195,9 +217,9 @@ __device__ __noinline__ float block_reduce(float v, float* red, int op /*0 max, 
 __device__ __noinline__ int block_min_int(int v, int* red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
-  __syncthreads();
+  cta_sync();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
+  cta_sync();
   int r = red[threadIdx.x & (NWARPS - 1)];
 #pragma unroll
   for (int o = NWARPS / 2; o > 0; o >>= 1) r = min(r, __shfl_xor_sync(0xffffffffu, r, o));
@@ -287,27 +309,33 @@ __device__ __forceinline__ int idiv_small(int a, int b) {  // exact for 0 <= a <
   return __float2int_rz(__fdividef((float)a + 0.5f, (float)b));
 }
 
-template <int NT>
-__device__ __forceinline__ void flush_acc(float (&acc)[2][NT][4], float* pp, int nct, int t, int g) {
+template <int NT, int NACC>
+__device__ __forceinline__ void flush_acc(float (&acc)[NACC][NT][4], float* pp, int nct, int t, int g) {
 #pragma unroll
   for (int n = 0; n < NT; ++n) {
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      v[q] = acc[0][n][q];
+#pragma unroll
+      for (int a = 1; a < NACC; ++a) v[q] += acc[a][n][q];
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) acc[a][n][q] = 0.f;
+    }
     if (n < nct) {
       const int col = n * 8 + 2 * t;
-      pp[(col)*PCOL + g] = acc[0][n][0] + acc[1][n][0];
-      pp[(col + 1) * PCOL + g] = acc[0][n][1] + acc[1][n][1];
-      pp[(col)*PCOL + g + 8] = acc[0][n][2] + acc[1][n][2];
-      pp[(col + 1) * PCOL + g + 8] = acc[0][n][3] + acc[1][n][3];
+      pp[(col)*PCOL + g] = v[0];
+      pp[(col + 1) * PCOL + g] = v[1];
+      pp[(col)*PCOL + g + 8] = v[2];
+      pp[(col + 1) * PCOL + g + 8] = v[3];
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) acc[0][n][q] = acc[1][n][q] = 0.f;
   }
 }
 
 // The phase body.  `m` is this CTA's meta of the phase (tiles owned, K blocks); the weights arrive through the ring.
 template <int NT>
-__device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const KParams& P, Ring& rg, const PMeta* meta, int niter,
-                                           unsigned char* smem, RoundTab* tab, uint32_t xbar, uint32_t& xpar,
-                                           uint64_t pol_keep, uint64_t pol_stream, int cp_phases) {
+__device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const KParams& P, Ring& rg, unsigned char* smem,
+                                           RoundTab* tab, uint32_t xbar, uint32_t& xpar) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int KB = m.kb, K = KB * 32, epi = ph.epi, ntc = m.ntc;
@@ -347,7 +375,7 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const
   }
   PROF_MARK(2);
   if (ntc <= 0) {
-    __syncthreads();
+    cta_sync();
     return;
   }
 
@@ -355,7 +383,7 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const
   const int rsh = swiglu ? 3 : 4;  // output rows per tile: 8 (gate/up pairs) or 16
 #pragma unroll 1
   for (int round = 0; round * 8 < ntc; ++round) {
-    if (round) __syncthreads();  // the previous round's epilogue still reads the round table and part
+    if (round) cta_sync();  // the previous round's epilogue still reads the round table and part
     const RunGeom rgm = q3ring::run_geom(ntc, KB, round, warp);
     const int TB = rgm.TB, upw = rgm.upw;
     const int tl0 = idiv_small(rgm.u0, KB);
@@ -381,16 +409,21 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const
         }
       }
     }
-    __syncthreads();  // x area + round table visible (also separates rounds: part is free again)
+    cta_sync();  // x area + round table visible (also separates rounds: part is free again)
 
-    // ---- main loop: this warp's run, piece by piece, out of its ring
+    // ---- main loop: this warp's run, piece by piece, out of its ring.  All fragment loads of a piece are issued
+    // before its MMAs, and consecutive MMAs go to independent accumulators (NACC sets), so neither the LDS latency
+    // nor the MMA latency serialises (measured before: ~280 cycles per 1 KB block with the naive order)
     {
-      float acc[2][NT][4];
+      constexpr int NACC = NT <= 2 ? 4 : 2;
+      float acc[NACC][NT][4];
 #pragma unroll
-      for (int n = 0; n < NT; ++n)
+      for (int a = 0; a < NACC; ++a)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[0][n][q] = acc[1][n][q] = 0.f;
-      long long wait_cycles = 0, comp_cycles = 0, prod_cycles = 0;
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[a][n][q] = 0.f;
+      long long wait_cycles = 0, comp_cycles = 0;
       PROF_MARK(8);
       int u = rgm.u0;
       int kbi = rgm.u0 - tl0 * KB;
@@ -402,63 +435,67 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const
         uint4 bq[4][NT];
         if (!staged) {  // B fragments straight from L2, issued before the slot wait
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < 4; ++i) {
+            int kk = kbi + i;  // may run past KB at a tile boundary: wrap
+            while (kk >= KB) kk -= KB;
 #pragma unroll
             for (int n = 0; n < NT; ++n) {
               const int col = n * 8 + g;
-              int kk = kbi + i;  // may run past KB at a tile boundary: wrap
-              if (kk >= KB) kk -= KB;
               bq[i][n] = (i < nb && n < nct && col < nc) ? ldcg16(src + (size_t)col * src_ld + kk * 32 + t * 8) : make_uint4(0, 0, 0, 0);
             }
+          }
         }
-        long long w0 = 0;
+        long long w0 = 0, w1 = 0;
         if (g_prof_row) w0 = clock64();
-        mbar_wait(rg.bars + 8u * rg.c_slot, (uint32_t)rg.c_par, P.st);
-        long long w1 = 0;
+        mbar_wait(rg.full + 8u * rg.c_slot, (uint32_t)rg.c_par, P.st);
         if (g_prof_row) { w1 = clock64(); if (tid == 0) wait_cycles += w1 - w0; }
         const uint32_t sp = rg.slots + (uint32_t)(rg.c_slot * rg.SB) * 1024u + (uint32_t)lane * 16u;
+        uint4 ra[4], sa[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i < nb) { ra[i] = lds128(sp + i * 1024); sa[i] = lds128(sp + i * 1024 + 512); }
+        }
+        if (staged) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i < nb) {
+              int kk = kbi + i;
+              while (kk >= KB) kk -= KB;
+#pragma unroll
+              for (int n = 0; n < NT; ++n)
+                if (n < nct) bq[i][n] = lds128(xs_sh + (uint32_t)((n * 8 + g) * xstride + kk * 64 + t * 16));
+            }
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (i < nb) {
-            const uint4 r = lds128(sp + i * 1024), s = lds128(sp + i * 1024 + 512);
 #pragma unroll
             for (int n = 0; n < NT; ++n) {
               if (n < nct) {
-                uint4 b;
-                if (staged) b = lds128(xs_sh + (uint32_t)((n * 8 + g) * xstride + kbi * 64 + t * 16));
-                else b = bq[i][n];
-                mma_bf16_16816(acc[i & 1][n], r.x, s.x, r.y, s.y, b.x, b.y);
-                mma_bf16_16816(acc[i & 1][n], r.z, s.z, r.w, s.w, b.z, b.w);
+                mma_bf16_16816(acc[(2 * i) % NACC][n], ra[i].x, sa[i].x, ra[i].y, sa[i].y, bq[i][n].x, bq[i][n].y);
+                mma_bf16_16816(acc[(2 * i + 1) % NACC][n], ra[i].z, sa[i].z, ra[i].w, sa[i].w, bq[i][n].z, bq[i][n].w);
               }
             }
             if (++kbi == KB) {  // tile boundary inside the run: spill this tile's partial sums
-              flush_acc<NT>(acc, pp + seg * (NT * 8) * PCOL, nct, t, g);
+              flush_acc<NT, NACC>(acc, pp + seg * (NT * 8) * PCOL, nct, t, g);
               kbi = 0;
               ++seg;
             }
           }
         }
-        __syncwarp();
-        ring_release(rg);
-        long long p0 = 0;
-        if (g_prof_row) p0 = clock64();
-        if (!(P.flags & 8) || rg.outstanding == 0) ring_produce(rg, meta, P, niter, warp, lane, pol_keep, pol_stream, cp_phases);
-        if (g_prof_row && tid == 0) { prod_cycles += clock64() - p0; comp_cycles += p0 - w1; }
+        ring_release(rg, lane);
+        if (g_prof_row && tid == 0) comp_cycles += clock64() - w1;
         u += nb;
       }
-      if (kbi != 0) flush_acc<NT>(acc, pp + seg * (NT * 8) * PCOL, nct, t, g);
-      if (P.flags & 8) {
-#pragma unroll 1
-        for (int i = 0; i < rg.R; ++i) ring_produce(rg, meta, P, niter, warp, lane, pol_keep, pol_stream, cp_phases);
-      }
-      if (tid == 0 && g_prof_row) {  // warp 0: [5] cycles waiting for ring data, [9] computing, [10] in ring_produce; [7] run finished
+      if (kbi != 0) flush_acc<NT, NACC>(acc, pp + seg * (NT * 8) * PCOL, nct, t, g);
+      if (tid == 0 && g_prof_row) {  // warp 0: [5] cycles waiting for ring data, [9] computing; [7] run finished
         g_prof_row[5] = (unsigned long long)wait_cycles;
         g_prof_row[9] = (unsigned long long)comp_cycles;
-        g_prof_row[10] = (unsigned long long)prod_cycles;
         PROF_MARK(7);
       }
     }
-    __syncthreads();
+    cta_sync();
     PROF_MARK(3);
     // ---- cross-warp reduce + epilogue, one output element per thread-iteration
 #pragma unroll 1
@@ -494,7 +531,7 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const
     }
     PROF_MARK(4);
   }
-  __syncthreads();
+  cta_sync();
 }
 
 }  // namespace

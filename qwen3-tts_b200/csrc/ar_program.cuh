@@ -5,8 +5,9 @@
 
 namespace {
 
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 256;                 // worker threads (8 consumer warps)
 constexpr int NWARPS = NTHREADS / 32;
+constexpr int CTA_THREADS = NTHREADS + 128;    // + one producer warp that owns the TMA weight stream
 constexpr int HD = 128;          // head_dim (required)
 constexpr int MAXB = Q3_MAX_BATCH;
 constexpr int MAXCOLS = 32;      // columns per pass (batch rows or prefill tokens)

@@ -20,13 +20,13 @@ __device__ __noinline__ float kth_largest(const float* sv, int V, int k, unsigne
   for (int pass = 3; pass >= 0; --pass) {
     const int shift = pass * 8;
     if (threadIdx.x < 256) hist[threadIdx.x] = 0;
-    __syncthreads();
+    cta_sync();
 #pragma unroll 1
     for (int i = threadIdx.x; i < V; i += NTHREADS) {
       const unsigned int key = fkey(sv[i]);
       if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
     }
-    __syncthreads();
+    cta_sync();
     // suffix counts over the 256 bins (8 warps)
     unsigned int cnt = 0, incl = 0;
     if (threadIdx.x < 256) {
@@ -40,7 +40,7 @@ __device__ __noinline__ float kth_largest(const float* sv, int V, int k, unsigne
       }
       if (ln == 0) sh[threadIdx.x >> 5] = (int)incl;  // warp totals
     }
-    __syncthreads();
+    cta_sync();
     if (threadIdx.x < 256) {
       unsigned int above = 0;
 #pragma unroll 1
@@ -49,11 +49,11 @@ __device__ __noinline__ float kth_largest(const float* sv, int V, int k, unsigne
       const unsigned int excl = incl - cnt;  // elements with digit > d
       if ((int)excl < k && k <= (int)incl) { sh[8] = threadIdx.x; sh[9] = k - (int)excl; }
     }
-    __syncthreads();
+    cta_sync();
     prefix |= ((unsigned int)sh[8]) << shift;
     mask |= 255u << shift;
     k = sh[9];
-    __syncthreads();
+    cta_sync();
   }
   const unsigned int u = (prefix & 0x80000000u) ? (prefix & 0x7fffffffu) : ~prefix;
   return __uint_as_float(u);
@@ -111,7 +111,7 @@ __device__ __noinline__ void sample_phase(const Phase& ph, const KParams& P, uns
     if (inv_t != 1.0f) s = s / inv_t;
     sv[i] = s;
   }
-  __syncthreads();
+  cta_sync();
 
   int tok;
   if (!do_sample) {
@@ -130,7 +130,7 @@ __device__ __noinline__ void sample_phase(const Phase& ph, const KParams& P, uns
 #pragma unroll 1
       for (int i = tid; i < V; i += NTHREADS)
         if (sv[i] < thr) sv[i] = -INFINITY;
-      __syncthreads();
+      cta_sync();
     }
     float mx = -INFINITY;
 #pragma unroll 1
@@ -142,7 +142,7 @@ __device__ __noinline__ void sample_phase(const Phase& ph, const KParams& P, uns
 #pragma unroll 1
       for (int i = tid; i < V; i += NTHREADS) { const float p = __expf(sv[i] - mx); pv[i] = p; tot += p; }
       tot = block_reduce(tot, red, 1);
-      __syncthreads();
+      cta_sync();
       unsigned int rm_mask = 0;  // removal flags stay in registers until every thread has finished reading pv/sv
       int slot = 0;
 #pragma unroll 1
@@ -163,12 +163,12 @@ __device__ __noinline__ void sample_phase(const Phase& ph, const KParams& P, uns
         }
         if (rm) rm_mask |= 1u << slot;
       }
-      __syncthreads();
+      cta_sync();
       slot = 0;
 #pragma unroll 1
       for (int i = tid; i < V; i += NTHREADS, ++slot)
         if (rm_mask & (1u << slot)) sv[i] = -INFINITY;
-      __syncthreads();
+      cta_sync();
     }
     // softmax + inverse CDF in token-id order (blocked mapping for the scan)
     const int E = (V + NTHREADS - 1) / NTHREADS;
@@ -184,9 +184,9 @@ __device__ __noinline__ void sample_phase(const Phase& ph, const KParams& P, uns
       const float n = __shfl_up_sync(0xffffffffu, incl, o);
       if (ln >= o) incl += n;
     }
-    __syncthreads();
+    cta_sync();
     if (ln == 31) red[wp] = incl;
-    __syncthreads();
+    cta_sync();
     float base = 0.f, total = 0.f;
 #pragma unroll 1
     for (int w = 0; w < NWARPS; ++w) { if (w < wp) base += red[w]; total += red[w]; }
@@ -213,7 +213,7 @@ __device__ __noinline__ void sample_phase(const Phase& ph, const KParams& P, uns
   if (talker) {
     const int was_finished = ldcgi(&st->finished[b]);
     if (was_finished) tok = P.eos;  // HF pads finished rows with pad_token_id (= eos)
-    __syncthreads();
+    cta_sync();
     if (tid == 0) {
       if (!was_finished) {
         if (tok == P.eos) { st->finished[b] = 1; st->n_valid[b] = fidx; }
@@ -243,7 +243,7 @@ __device__ __noinline__ void sample_phase(const Phase& ph, const KParams& P, uns
         if (j == 1) row[0] = ldcgi(&st->cur[b][0]);
       }
     }
-    __syncthreads();
+    cta_sync();
     const int Vc = P.cp.vocab;
     if (j < P.G - 1) {
       // input of the next pass: codec_embedding[j-1](c_j)  (:1281)
@@ -261,7 +261,7 @@ __device__ __noinline__ void sample_phase(const Phase& ph, const KParams& P, uns
                             : P.tts_pad;
       int* codes = reinterpret_cast<int*>(hist);  // smem scratch: the 16 codes of this frame
       if (tid < P.G) codes[tid] = (tid == j) ? tok : ldcgi(&st->cur[b][tid]);
-      __syncthreads();
+      cta_sync();
 #pragma unroll 1
       for (int i = tid; i < H; i += NTHREADS) {
         float s = bf2f(P.emb_t[(size_t)codes[0] * H + i]);

@@ -221,8 +221,10 @@ def _full_shape_case(model, lens, N, seed):
         r = ref.record["talker_logits"][f]
         scale = float(np.std(r))
         d = np.abs(tl[f] - r)
-        # calibration: the oracle's own bf16-vs-fp32 gap at this shape is max 0.11*std, mean 0.024*std
-        assert d.max() < 0.2 * scale and d.mean() < 0.05 * scale, (model, B, "talker", f, d.max(), d.mean(), scale)
+        # calibration (tools/calibrate_tolerance.py -> profiles/r02_tolerance_calibration.txt): PyTorch's own bf16 run
+        # of these shapes (ctx 200-230, 8 frames) sits at max 0.18*std (talker) / 0.21*std (code predictor), mean
+        # 0.033*std from the fp32 oracle; the engine is held to 1.5x that maximum and to the same mean band
+        assert d.max() < 0.3 * scale and d.mean() < 0.05 * scale, (model, B, "talker", f, d.max(), d.mean(), scale)
         worst = max(worst, d.max() / scale)
         srt = np.sort(r, -1)
         margin = srt[..., -1] - srt[..., -2]
@@ -233,7 +235,7 @@ def _full_shape_case(model, lens, N, seed):
             r = ref.record["cp_logits"][f * (G - 1) + j]
             scale = float(np.std(r))
             d = np.abs(cl[f, j] - r)
-            assert d.max() < 0.2 * scale and d.mean() < 0.05 * scale, (model, B, "cp", f, j, d.max(), d.mean())
+            assert d.max() < 0.3 * scale and d.mean() < 0.05 * scale, (model, B, "cp", f, j, d.max(), d.mean())
             worst = max(worst, d.max() / scale)
     # free-running greedy from the same prompts: report the exact-match rate against the oracle's own greedy codes
     out = eng.generate(embs, trail, pad, Hh.to_pkg_sampling(sp))
