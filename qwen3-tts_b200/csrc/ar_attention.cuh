@@ -70,7 +70,7 @@ __device__ __forceinline__ AttnUnit attn_unit(const Phase& ph, const KParams& P,
   return u;
 }
 
-constexpr int KVWIN = 96;                                   // cached K/V rows per unit held in shared memory
+constexpr int KVWIN = 60;                                   // cached K/V rows per unit held in shared memory
 constexpr int ATT_QS_BYTES = 2 * RMAX * HD * 4;             // fp32 queries [nq<=2][RMAX][128]
 constexpr int ATT_RED_BYTES = 32 * RMAX * 130 * 4;          // per-half-warp partials
 constexpr int ATT_WIN_OFF = ATT_QS_BYTES + ATT_RED_BYTES;   // K window, then V window (bf16 [KVWIN][128] each)
@@ -99,11 +99,11 @@ __device__ __forceinline__ void attn_window_issue(const Phase& ph, const KParams
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-__device__ __noinline__ void attn_prefetch(const Phase& ph, const KParams& P, unsigned char* smem, int frame) {
+__device__ __forceinline__ void attn_prefetch(const Phase& ph, const KParams& P, unsigned char* smem, int frame) {
   attn_window_issue(ph, P, smem, frame, (int)blockIdx.x);
 }
 
-__device__ __noinline__ void attn_phase(const Phase& ph, const KParams& P, unsigned char* smem, int frame) {
+__device__ __forceinline__ void attn_phase(const Phase& ph, const KParams& P, unsigned char* smem, int frame) {
   const StackDev& S = ph.stack == 0 ? P.talker : P.cp;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nh = S.nh, nkv = S.nkv, layers = S.layers, cap = S.cap;

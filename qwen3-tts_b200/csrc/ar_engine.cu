@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) q3_step_kernel(const __grid_co
   if (warp >= NWARPS) {
     // ================= producer warp: the TMA weight stream of all eight consumer rings =================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
-    if (warp == NWARPS) producer_loop(P, meta, niter, ring0, full0, empty0, &s_stop, s_issued, P.mode == 1 ? P.cp_phases : 0);
+    if (warp == CTA_THREADS / 32 - 1) producer_loop(P, meta, niter, ring0, full0, empty0, &s_stop, s_issued, P.mode == 1 ? P.cp_phases : 0);
   } else {
     // ================= 8 consumer warps: the phase program =================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) q3_step_kernel(const __grid_co
           PROF_MARK(6);
         }
         const int type = ph.type;
-        if (type == PH_GEMV) gemv_phase<NT>(ph, meta[pi], P, rg, smem, &s_tab, xbar, xpar);
+        if (type == PH_GEMV) xpar = gemv_phase<NT>(ph, meta[pi], P, rg, smem, &s_tab, xbar, xpar);
         else if (type == PH_ATTN) attn_phase(ph, P, smem + P.plan.x_off, frame);
         else sample_phase(ph, P, smem + P.plan.x_off, frame, P.mode == 0);
         if (dhave) reinterpret_cast<uint32_t*>(&s_ph[slot ^ 1])[tid] = dreg;
@@ -463,11 +463,17 @@ static int make_smem_plan(q3_engine* e, std::vector<Phase>& prog, int B, int nt,
   pl.ring_off = up(pl.nw_off + NW_BYTES, 1024);
   const int meta_bytes = up((int)prog.size() * (int)sizeof(q3ring::PMeta), 16);
   const int bar_bytes = 8 * (2 * NWARPS * MAX_SLOTS + 1) + 8;  // full + empty barrier per ring slot, the x barrier
-  const int avail = e->max_dyn_smem - pl.ring_off - meta_bytes - bar_bytes;
+  // batch classes 1-2 stay under the 196 KB carve-out (195 KB per CTA) so that 32 KB of the SM remain L1: the phase
+  // functions' stack traffic then hits L1 instead of making an L2 round trip each (Q3_SMEM_FULL=1 lifts the cap: A/B)
+  int limit = e->max_dyn_smem;
+  if (nt <= 2 && !getenv("Q3_SMEM_FULL")) limit = std::min(limit, 195 * 1024 - (SMEM_OPTIN - e->max_dyn_smem) - 256);
+  const int avail = limit - pl.ring_off - meta_bytes - bar_bytes;
+  int slot_cap = MAX_SLOTS;
+  if (const char* f = getenv("Q3_RING_SLOTS")) slot_cap = std::max(2, std::min(MAX_SLOTS, atoi(f)));
   pl.slot_blocks = 0;
   for (int sb : {4, 2, 1}) {
     const int r = avail / (NWARPS * sb * 1024);
-    if (r >= 2) { pl.slot_blocks = sb; pl.nslots = std::min(r, MAX_SLOTS); break; }
+    if (r >= 2) { pl.slot_blocks = sb; pl.nslots = std::min(r, slot_cap); break; }
   }
   Q3_REQUIRE(pl.slot_blocks > 0, "no shared memory left for the weight rings (x area %d B, batch class %d)", pl.x_bytes, nt);
   pl.meta_off = pl.ring_off + NWARPS * pl.nslots * pl.slot_blocks * 1024;

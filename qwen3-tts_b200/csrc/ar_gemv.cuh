@@ -94,14 +94,16 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: a waiting thread sleeps in hardware (woken by the phase completion) instead of
+// spinning through issue slots that the other warps of its scheduler need
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(done)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(2000u)
       : "memory");
   return done != 0;
 }
@@ -309,6 +311,22 @@ __device__ __forceinline__ int idiv_small(int a, int b) {  // exact for 0 <= a <
   return __float2int_rz(__fdividef((float)a + 0.5f, (float)b));
 }
 
+// B fragments of `count` (<= 4) consecutive k-blocks starting at block kb0 (wrapping at KB) straight from global memory
+template <int NT>
+__device__ __forceinline__ void load_bfrags(uint4 (&dst)[4][NT], const bf16* __restrict__ src, int src_ld, int nc, int nct, int kb0,
+                                            int KB, int count, int g, int t) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int kk = kb0 + i;
+    while (kk >= KB) kk -= KB;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const int col = n * 8 + g;
+      dst[i][n] = (i < count && n < nct && col < nc) ? ldcg16(src + (size_t)col * src_ld + kk * 32 + t * 8) : make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
 template <int NT, int NACC>
 __device__ __forceinline__ void flush_acc(float (&acc)[NACC][NT][4], float* pp, int nct, int t, int g) {
 #pragma unroll
@@ -334,8 +352,8 @@ __device__ __forceinline__ void flush_acc(float (&acc)[NACC][NT][4], float* pp, 
 
 // The phase body.  `m` is this CTA's meta of the phase (tiles owned, K blocks); the weights arrive through the ring.
 template <int NT>
-__device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const KParams& P, Ring& rg, unsigned char* smem,
-                                           RoundTab* tab, uint32_t xbar, uint32_t& xpar) {
+__device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, const KParams& P, Ring& rg, unsigned char* smem,
+                                               RoundTab* tab, uint32_t xbar, uint32_t xpar) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int KB = m.kb, K = KB * 32, epi = ph.epi, ntc = m.ntc;
@@ -376,7 +394,7 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const
   PROF_MARK(2);
   if (ntc <= 0) {
     cta_sync();
-    return;
+    return xpar;
   }
 
   const bool swiglu = epi == EPI_SWIGLU;
@@ -397,7 +415,7 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const
     int tbl = 0;
     while ((1 << tbl) < TB) ++tbl;
     const int nelem = nc << (rsh + tbl);
-    float resid[2] = {0.f, 0.f};
+    float resid0 = 0.f, resid1 = 0.f;  // (two scalars, not an array: a dynamically indexed array would live in local memory)
     if (epi == EPI_RESID) {
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -405,7 +423,8 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const
         const int tl = (e >> rsh) & ((1 << tbl) - 1);
         if (e < nelem && tl < TB) {
           const int row = (t0 + round * 8 + tl) * 16 + (e & 15);
-          resid[i] = bf2f(ldcg_bf16(reinterpret_cast<const bf16*>(dst) + (size_t)(e >> (rsh + tbl)) * dst_ld + row));
+          const float v = bf2f(ldcg_bf16(reinterpret_cast<const bf16*>(dst) + (size_t)(e >> (rsh + tbl)) * dst_ld + row));
+          if (i == 0) resid0 = v; else resid1 = v;
         }
       }
     }
@@ -429,21 +448,18 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const
       int kbi = rgm.u0 - tl0 * KB;
       int seg = 0;
       float* pp = part + ((warp * 2) * (NT * 8)) * PCOL;
+      // B fragments of an un-staged input (K too large for the x area) come straight from L2, one piece AHEAD of the
+      // MMAs that use them (double buffer in registers): only the first piece of a run exposes the L2 latency
+      uint4 bq[4][NT];
+      if (!staged) load_bfrags<NT>(bq, src, src_ld, nc, nct, kbi, KB, q3ring::imin(rg.SB, rgm.u1 - u), g, t);
 #pragma unroll 1
       while (u < rgm.u1) {
         const int nb = q3ring::imin(rg.SB, rgm.u1 - u);
-        uint4 bq[4][NT];
-        if (!staged) {  // B fragments straight from L2, issued before the slot wait
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            int kk = kbi + i;  // may run past KB at a tile boundary: wrap
-            while (kk >= KB) kk -= KB;
-#pragma unroll
-            for (int n = 0; n < NT; ++n) {
-              const int col = n * 8 + g;
-              bq[i][n] = (i < nb && n < nct && col < nc) ? ldcg16(src + (size_t)col * src_ld + kk * 32 + t * 8) : make_uint4(0, 0, 0, 0);
-            }
-          }
+        uint4 bnx[4][NT];
+        if (!staged && u + nb < rgm.u1) {
+          int kn = kbi + nb;
+          while (kn >= KB) kn -= KB;
+          load_bfrags<NT>(bnx, src, src_ld, nc, nct, kn, KB, q3ring::imin(rg.SB, rgm.u1 - u - nb), g, t);
         }
         long long w0 = 0, w1 = 0;
         if (g_prof_row) w0 = clock64();
@@ -485,6 +501,12 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const
           }
         }
         ring_release(rg, lane);
+        if (!staged) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int n = 0; n < NT; ++n) bq[i][n] = bnx[i][n];
+        }
         if (g_prof_row && tid == 0) comp_cycles += clock64() - w1;
         u += nb;
       }
@@ -507,7 +529,7 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const
       const int tile = t0 + round * 8 + tl;
       const int row = tile * 16 + r;
       float rs = 0.f;
-      if (epi == EPI_RESID) rs = it < 2 ? resid[it & 1] : bf2f(ldcg_bf16(reinterpret_cast<const bf16*>(dst) + (size_t)col * dst_ld + row));
+      if (epi == EPI_RESID) rs = it == 0 ? resid0 : it == 1 ? resid1 : bf2f(ldcg_bf16(reinterpret_cast<const bf16*>(dst) + (size_t)col * dst_ld + row));
       float s0 = 0.f, s1 = 0.f;
       const int wf = tab->wf[tl], wl = tab->wl[tl];
 #pragma unroll 4
@@ -532,6 +554,7 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, const PMeta m, const
     PROF_MARK(4);
   }
   cta_sync();
+  return xpar;
 }
 
 }  // namespace

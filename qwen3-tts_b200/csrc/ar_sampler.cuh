@@ -59,7 +59,7 @@ __device__ __noinline__ float kth_largest(const float* sv, int V, int k, unsigne
   return __uint_as_float(u);
 }
 
-__device__ __noinline__ void sample_phase(const Phase& ph, const KParams& P, unsigned char* smem, int frame, bool in_prefill) {
+__device__ __forceinline__ void sample_phase(const Phase& ph, const KParams& P, unsigned char* smem, int frame, bool in_prefill) {
   const int b = blockIdx.x;
   DevState* st = P.st;
   const int B = P.B;

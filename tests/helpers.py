@@ -146,6 +146,7 @@ def report_parity(name, record):
     """Parity figures the GPU tests measure (free-running exact-match rates, worst logit errors): printed, and
     collected into gpurun_out/parity_report.json so a GPU run leaves them behind as an artifact."""
     import json, os
+    record = {k: (float(v) if isinstance(v, (np.floating, float)) else int(v) if isinstance(v, (np.integer,)) else v) for k, v in record.items()}
     print(f"[parity] {name}: {json.dumps(record)}")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = os.path.join(root, "gpurun_out")
