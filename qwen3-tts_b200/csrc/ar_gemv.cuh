@@ -311,6 +311,27 @@ __device__ __forceinline__ int idiv_small(int a, int b) {  // exact for 0 <= a <
   return __float2int_rz(__fdividef((float)a + 0.5f, (float)b));
 }
 
+// One full ring piece (4 k32-blocks of one tile) against the staged activations: all fragment loads first, then the
+// MMAs.  A block is two 512-byte halves; lane l's 16 bytes of a half ARE the four A registers of one m16n8k16 MMA
+// (pack_weight_kernel), so no register shuffling sits between the loads and the tensor pipe.
+template <int NT, int NACC, int NCT>
+__device__ __forceinline__ void piece4(float (&acc)[NACC][NT][4], uint32_t sp, uint32_t xb, int xstride) {
+  uint4 a1[4], a2[4], b[4][NCT];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { a1[i] = lds128(sp + i * 1024); a2[i] = lds128(sp + i * 1024 + 512); }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int n = 0; n < NCT; ++n) b[i][n] = lds128(xb + (uint32_t)(i * 64 + n * 8 * xstride));
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int n = 0; n < NCT; ++n) {
+      mma_bf16_16816(acc[(2 * i) % NACC][n], a1[i].x, a1[i].y, a1[i].z, a1[i].w, b[i][n].x, b[i][n].y);
+      mma_bf16_16816(acc[(2 * i + 1) % NACC][n], a2[i].x, a2[i].y, a2[i].z, a2[i].w, b[i][n].z, b[i][n].w);
+    }
+}
+
 // B fragments of `count` (<= 4) consecutive k-blocks starting at block kb0 (wrapping at KB) straight from global memory
 template <int NT>
 __device__ __forceinline__ void load_bfrags(uint4 (&dst)[4][NT], const bf16* __restrict__ src, int src_ld, int nc, int nct, int kb0,
@@ -442,12 +463,13 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
         for (int n = 0; n < NT; ++n)
 #pragma unroll
           for (int q = 0; q < 4; ++q) acc[a][n][q] = 0.f;
-      long long wait_cycles = 0, comp_cycles = 0;
+      long long wait_cycles = 0;
       PROF_MARK(8);
       int u = rgm.u0;
       int kbi = rgm.u0 - tl0 * KB;
       int seg = 0;
       float* pp = part + ((warp * 2) * (NT * 8)) * PCOL;
+      const uint32_t xb0 = xs_sh + (uint32_t)(g * xstride + t * 16);  // this lane's B-fragment base (column g of n-tile 0)
       // B fragments of an un-staged input (K too large for the x area) come straight from L2, one piece AHEAD of the
       // MMAs that use them (double buffer in registers): only the first piece of a run exposes the L2 latency
       uint4 bq[4][NT];
@@ -461,42 +483,58 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
           while (kn >= KB) kn -= KB;
           load_bfrags<NT>(bnx, src, src_ld, nc, nct, kn, KB, q3ring::imin(rg.SB, rgm.u1 - u - nb), g, t);
         }
-        long long w0 = 0, w1 = 0;
+        long long w0 = 0;
         if (g_prof_row) w0 = clock64();
         mbar_wait(rg.full + 8u * rg.c_slot, (uint32_t)rg.c_par, P.st);
-        if (g_prof_row) { w1 = clock64(); if (tid == 0) wait_cycles += w1 - w0; }
+        if (g_prof_row && tid == 0) wait_cycles += clock64() - w0;
         const uint32_t sp = rg.slots + (uint32_t)(rg.c_slot * rg.SB) * 1024u + (uint32_t)lane * 16u;
-        uint4 ra[4], sa[4];
+        if (staged && nb == 4 && kbi + 4 <= KB) {
+          // fast path (every shipped shape: runs and tiles are multiples of 4 blocks): a full piece inside one tile.
+          // 8 A loads + the B loads are issued back to back, then 8 MMAs per n-tile on 4 independent accumulators
+          const uint32_t xb = xb0 + (uint32_t)kbi * 64u;
+          if (nct == 1) piece4<NT, NACC, 1>(acc, sp, xb, xstride);
+          else if (nct == 2) piece4<NT, NACC, (NT >= 2 ? 2 : 1)>(acc, sp, xb, xstride);
+          else piece4<NT, NACC, NT>(acc, sp, xb, xstride);
+          kbi += 4;
+          if (kbi == KB) {
+            flush_acc<NT, NACC>(acc, pp + seg * (NT * 8) * PCOL, nct, t, g);
+            kbi = 0;
+            ++seg;
+          }
+        } else {
+          // general path: partial pieces, a tile boundary inside the piece, un-staged inputs
+          uint4 am1[4], am2[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (i < nb) { ra[i] = lds128(sp + i * 1024); sa[i] = lds128(sp + i * 1024 + 512); }
-        }
-        if (staged) {
+          for (int i = 0; i < 4; ++i) {
+            if (i < nb) { am1[i] = lds128(sp + i * 1024); am2[i] = lds128(sp + i * 1024 + 512); }
+          }
+          if (staged) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (i < nb) {
+                int kk = kbi + i;
+                while (kk >= KB) kk -= KB;
+#pragma unroll
+                for (int n = 0; n < NT; ++n)
+                  if (n < nct) bq[i][n] = lds128(xb0 + (uint32_t)(n * 8 * xstride + kk * 64));
+              }
+            }
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             if (i < nb) {
-              int kk = kbi + i;
-              while (kk >= KB) kk -= KB;
 #pragma unroll
-              for (int n = 0; n < NT; ++n)
-                if (n < nct) bq[i][n] = lds128(xs_sh + (uint32_t)((n * 8 + g) * xstride + kk * 64 + t * 16));
-            }
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (i < nb) {
-#pragma unroll
-            for (int n = 0; n < NT; ++n) {
-              if (n < nct) {
-                mma_bf16_16816(acc[(2 * i) % NACC][n], ra[i].x, sa[i].x, ra[i].y, sa[i].y, bq[i][n].x, bq[i][n].y);
-                mma_bf16_16816(acc[(2 * i + 1) % NACC][n], ra[i].z, sa[i].z, ra[i].w, sa[i].w, bq[i][n].z, bq[i][n].w);
+              for (int n = 0; n < NT; ++n) {
+                if (n < nct) {
+                  mma_bf16_16816(acc[(2 * i) % NACC][n], am1[i].x, am1[i].y, am1[i].z, am1[i].w, bq[i][n].x, bq[i][n].y);
+                  mma_bf16_16816(acc[(2 * i + 1) % NACC][n], am2[i].x, am2[i].y, am2[i].z, am2[i].w, bq[i][n].z, bq[i][n].w);
+                }
               }
-            }
-            if (++kbi == KB) {  // tile boundary inside the run: spill this tile's partial sums
-              flush_acc<NT, NACC>(acc, pp + seg * (NT * 8) * PCOL, nct, t, g);
-              kbi = 0;
-              ++seg;
+              if (++kbi == KB) {  // tile boundary inside the run: spill this tile's partial sums
+                flush_acc<NT, NACC>(acc, pp + seg * (NT * 8) * PCOL, nct, t, g);
+                kbi = 0;
+                ++seg;
+              }
             }
           }
         }
@@ -507,13 +545,11 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
 #pragma unroll
             for (int n = 0; n < NT; ++n) bq[i][n] = bnx[i][n];
         }
-        if (g_prof_row && tid == 0) comp_cycles += clock64() - w1;
         u += nb;
       }
       if (kbi != 0) flush_acc<NT, NACC>(acc, pp + seg * (NT * 8) * PCOL, nct, t, g);
-      if (tid == 0 && g_prof_row) {  // warp 0: [5] cycles waiting for ring data, [9] computing; [7] run finished
+      if (tid == 0 && g_prof_row) {  // warp 0: [5] cycles waiting for ring data; [7] run finished
         g_prof_row[5] = (unsigned long long)wait_cycles;
-        g_prof_row[9] = (unsigned long long)comp_cycles;
         PROF_MARK(7);
       }
     }

@@ -144,17 +144,27 @@ __global__ void bf16_to_f32_kernel(const bf16* __restrict__ src, float* __restri
 }
 
 __global__ void pack_weight_kernel(const bf16* __restrict__ src, uint4* __restrict__ dst, int N, int K) {
-  // one thread per 16-byte chunk of the destination
+  // one thread per 16-byte chunk of the destination.  Block (tile, kb) = 16 rows x 32 k = 1 KB = two 512-byte halves;
+  // chunk `lane` (g = lane/4, t = lane%4) of half h holds the four A registers of MMA h of that lane:
+  //   { W[g][k0..k0+1], W[g+8][k0..k0+1], W[g][k0+2..k0+3], W[g+8][k0+2..k0+3] },  k0 = kb*32 + t*8 + h*4
+  // (the K permutation "lane t owns k t*8..t*8+7" is shared with the B fragments, which read 16 contiguous bytes of x)
   const size_t total = (size_t)N * K / 8;
   const int KB = K / 32;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t blk = i / 64;         // (tile, kb)
-    const int within = (int)(i % 64);  // half j (32 chunks each), then g*4 + t
-    const int j = within / 32, g = (within % 32) / 4, t = within % 4;
+    const int within = (int)(i % 64);
+    const int h = within / 32, g = (within % 32) / 4, t = within % 4;
     const size_t tile = blk / KB;
     const int kb = (int)(blk % KB);
-    const size_t row = tile * 16 + j * 8 + g;
-    dst[i] = *reinterpret_cast<const uint4*>(src + row * K + kb * 32 + t * 8);
+    const int k0 = kb * 32 + t * 8 + h * 4;
+    const bf16* r0 = src + (tile * 16 + g) * K + k0;
+    const bf16* r1 = src + (tile * 16 + g + 8) * K + k0;
+    uint4 o;
+    o.x = *reinterpret_cast<const uint32_t*>(r0);
+    o.y = *reinterpret_cast<const uint32_t*>(r1);
+    o.z = *reinterpret_cast<const uint32_t*>(r0 + 2);
+    o.w = *reinterpret_cast<const uint32_t*>(r1 + 2);
+    dst[i] = o;
   }
 }
 

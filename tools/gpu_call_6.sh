@@ -1,0 +1,15 @@
+#!/usr/bin/env bash
+set -u
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_ar.py -x -q -k "tiny or large_batch or free_running or sampler or long_context or two_frames" > gpurun_out/t_ar_tiny.log 2>&1; tail -4 gpurun_out/t_ar_tiny.log
+timeout 200 python bench.py --steps 2 --warmup 1 --no-extras --no-cpu-baseline --no-parity-check > gpurun_out/bench_d.json 2> gpurun_out/bench_d.err
+python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/bench_d.json"))
+    print("value", round(d["value"], 1), "ms/frame-step", round(d["roofline"]["ms_per_frame_step"], 3), "frac", round(d["roofline"]["frac"], 4), d["breakdown_ms_per_step"], "first_packet", round(d["first_packet_ms"] or 0, 1))
+except Exception as e:
+    print("bench failed", e); print(open("gpurun_out/bench_d.err").read()[-1500:])
+PY
+timeout 200 python tools/critical_path.py --batch 8 > gpurun_out/critical_b8.txt 2>&1; tail -14 gpurun_out/critical_b8.txt
+timeout 300 python tools/diag_free_run.py 32 > gpurun_out/diag32.txt 2>&1; tail -30 gpurun_out/diag32.txt
