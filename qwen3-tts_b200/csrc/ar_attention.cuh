@@ -42,33 +42,9 @@ __device__ __noinline__ void norm_rope_vec(const bf16* src, const bf16* nw, floa
 
 // ---- unit geometry: one (sequence, kv head, context split) per CTA-iteration
 struct AttnUnit {
-  int seq, kvh, sp, nsplit, q0, nq, qstride, ctx_end, s0, s1;
+  int seq, kvh, sp, nsplit, q0, nq, qstride, ctx_end, s0, s1, units;
 };
-
-__device__ __forceinline__ int attn_nsplit(const Phase& ph, const KParams& P, const StackDev& S, int frame) {
-  if (ph.seqmode != SEQ_DECODE) return 1;
-  int cmax = 0;
-  for (int b = 0; b < P.B; ++b) cmax = max(cmax, P.len0[b]);
-  cmax += frame + 1;
-  const int byctx = (cmax + 127) >> 7;
-  const int bygrid = (int)gridDim.x / (P.B * S.nkv);
-  return max(1, min(min(byctx, bygrid), MAXSPLIT));
-}
-
-__device__ __forceinline__ AttnUnit attn_unit(const Phase& ph, const KParams& P, const StackDev& S, int frame, int nsplit, int unit) {
-  AttnUnit u;
-  u.nsplit = nsplit;
-  u.sp = unit % nsplit;
-  u.kvh = (unit / nsplit) % S.nkv;
-  const int si = unit / (nsplit * S.nkv);
-  u.seq = si; u.q0 = si;
-  if (ph.seqmode == SEQ_CP) { u.nq = ph.nq; u.qstride = P.B; u.ctx_end = ph.ctx_end; }
-  else { u.nq = 1; u.qstride = 0; u.ctx_end = P.len0[si] + frame + 1; }
-  const int SL = (u.ctx_end + nsplit - 1) / nsplit;
-  u.s0 = u.sp * SL;
-  u.s1 = min(u.ctx_end, u.s0 + SL);
-  return u;
-}
+__shared__ AttnUnit s_au;  // geometry of the unit whose K/V window is (being) loaded; written by attn_window_issue
 
 constexpr int KVWIN = 60;                                   // cached K/V rows per unit held in shared memory
 constexpr int ATT_QS_BYTES = 2 * RMAX * HD * 4;             // fp32 queries [nq<=2][RMAX][128]
@@ -76,14 +52,32 @@ constexpr int ATT_RED_BYTES = 32 * RMAX * 130 * 4;          // per-half-warp par
 constexpr int ATT_WIN_OFF = ATT_QS_BYTES + ATT_RED_BYTES;   // K window, then V window (bf16 [KVWIN][128] each)
 static_assert(ATT_WIN_OFF % 16 == 0 && ATT_WIN_OFF + 2 * KVWIN * HD * 2 <= ATT_SMEM, "attention shared-memory layout");
 
-// K/V rows [s0, min(s1, first new position, s0+KVWIN)) of `unit` -> the shared-memory window, asynchronously
-// (cp.async, L2 -> smem).  They were written in earlier phases, so this runs BEFORE the grid barrier that
-// precedes the attention phase: by the time q/k of the new token are normalised the cached rows are on chip.
-__device__ __forceinline__ void attn_window_issue(const Phase& ph, const KParams& P, unsigned char* smem, int frame, int unit) {
+// Geometry of `unit` -> s_au, and its cached K/V rows [s0, min(s1, first new position, s0+KVWIN)) -> the shared-memory
+// window, asynchronously (cp.async, L2 -> smem).  Those rows were written in earlier phases, so for a CTA's first unit
+// this runs BEFORE the grid barrier that precedes the attention phase: by the time q/k of the new token are
+// normalised the cached rows are on chip.  One copy of this code (noinline): it is called from the pre-barrier hook
+// and from the unit loop, and instruction-cache footprint is what bounds the frame loop's phase overheads.
+__device__ __noinline__ void attn_window_issue(const Phase& ph, const KParams& P, unsigned char* smem, int frame, int unit) {
   const StackDev& S = ph.stack == 0 ? P.talker : P.cp;
-  const int nsplit = attn_nsplit(ph, P, S, frame);
-  if (unit < P.B * S.nkv * nsplit) {
-    const AttnUnit u = attn_unit(ph, P, S, frame, nsplit, unit);
+  int nsplit = 1;
+  if (ph.seqmode == SEQ_DECODE) {
+    const int cmax = P.max_len0 + frame + 1;
+    nsplit = max(1, min(min((cmax + 127) >> 7, (int)gridDim.x / (P.B * S.nkv)), MAXSPLIT));
+  }
+  AttnUnit u;
+  u.nsplit = nsplit;
+  u.units = P.B * S.nkv * nsplit;
+  u.sp = unit % nsplit;
+  u.kvh = (unit / nsplit) % S.nkv;
+  const int si = min(unit / (nsplit * S.nkv), P.B - 1);
+  u.seq = si; u.q0 = si;
+  if (ph.seqmode == SEQ_CP) { u.nq = ph.nq; u.qstride = P.B; u.ctx_end = ph.ctx_end; }
+  else { u.nq = 1; u.qstride = 0; u.ctx_end = P.len0[si] + frame + 1; }
+  const int SL = (u.ctx_end + nsplit - 1) / nsplit;
+  u.s0 = u.sp * SL;
+  u.s1 = min(u.ctx_end, u.s0 + SL);
+  if (threadIdx.x == 0) s_au = u;
+  if (unit < u.units) {
     const int hi = min(min(u.s1, u.ctx_end - u.nq), u.s0 + KVWIN);
     const int n = hi - u.s0;
     const size_t base = ((((size_t)u.seq * S.layers + ph.layer) * S.nkv + u.kvh) * (size_t)S.cap + u.s0) * HD;
@@ -113,8 +107,6 @@ __device__ __forceinline__ void attn_phase(const Phase& ph, const KParams& P, un
   const int layer = ph.layer;
   const float eps = S.eps;
   const bf16 *qn = ph.qn, *kn = ph.kn;
-  const int nsplit = attn_nsplit(ph, P, S, frame);
-  const int units = B * nkv * nsplit;
 
   float* qs = reinterpret_cast<float*>(smem);                 // [nq<=2][RMAX][128]
   float* red = qs + 2 * RMAX * HD;                            // [32 halfwarps][RMAX][130]
@@ -122,13 +114,17 @@ __device__ __forceinline__ void attn_phase(const Phase& ph, const KParams& P, un
   bf16* vwin = kwin + KVWIN * HD;
   __shared__ int s_ticket;
 
+  // s_au holds the geometry of this CTA's first unit (written before the preceding grid barrier, which ended in a
+  // CTA-wide sync); later units (B*nkv*nsplit > grid) compute theirs and fetch their window inside the loop
 #pragma unroll 1
-  for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
-    if (unit != (int)blockIdx.x) {  // later units of this CTA (B*nkv*nsplit > grid): fetch their window now
+  for (int unit = blockIdx.x; unit < s_au.units; unit += gridDim.x) {
+    if (unit != (int)blockIdx.x) {
       cta_sync();
       attn_window_issue(ph, P, smem, frame, unit);
+      cta_sync();
     }
-    const AttnUnit U = attn_unit(ph, P, S, frame, nsplit, unit);
+    const AttnUnit U = s_au;
+    const int nsplit = U.nsplit;
     const int sp = U.sp, kvh = U.kvh, seq = U.seq, q0 = U.q0, nq = U.nq, qstride = U.qstride, ctx_end = U.ctx_end;
     const int s0 = U.s0, s1 = U.s1;
     bf16* kc = S.kc + (((size_t)seq * layers + layer) * nkv + kvh) * (size_t)cap * HD;

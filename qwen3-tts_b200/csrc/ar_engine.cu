@@ -673,6 +673,7 @@ static int launch_program(q3_engine* e, int off, int n, int mode, int max_iters,
   P.has_proj = e->cfg.has_cp_projection; P.sp = e->sp;
   P.B = e->B;
   for (int b = 0; b < MAXB; ++b) { P.len0[b] = e->len0[b]; P.trailing_len[b] = e->trailing_len[b]; }
+  P.max_len0 = e->max_len0;
   P.emb_t = e->plain["talker.codec_embedding"]; P.emb_cp = e->plain["cp.codec_embedding"];
   P.x_cp = e->cfg.has_cp_projection ? e->x_cp : e->cp.h; P.past_hidden = e->past_hidden; P.trailing = e->trailing; P.trailing_stride = e->trailing_cap;
   if (e->proj_tab) { P.cp_next = e->proj_tab; P.cp_next_dst = e->cp.h; P.cp_next_w = e->cfg.cp.hidden_size; }

@@ -244,59 +244,47 @@ __device__ __forceinline__ uint32_t norm_pair(uint32_t x2, uint32_t w2, float in
   return *reinterpret_cast<uint32_t*>(&r);
 }
 
-// stage x (optionally RMS-normed) into smem as bf16 [col][K] (rows skewed by 64 B).  One warp per column; a lane
-// issues up to 8 independent 16-byte loads per pass before touching the data; the RMSNorm runs on the registers
-// (sum of squares -> warp reduce -> scale) and the result is written to smem once.  The norm weights sit in nw_s
-// (fetched before the preceding grid barrier).
-__device__ __forceinline__ void stage_columns(const bf16* __restrict__ src, int src_ld, bool normed, float eps,
-                                              bf16* __restrict__ save, int K, int nc, char* __restrict__ xs, int xstride,
-                                              const uint4* __restrict__ nw_s) {
+// stage RMS-normed x into smem as bf16 [col][K] (rows skewed by 64 B).  One warp per column; a lane issues its (up to 8)
+// independent 16-byte loads first, the RMSNorm runs on the registers (sum of squares -> warp reduce -> scale) and the
+// result is written to smem once.  The norm weights sit in nw_s (fetched before the preceding grid barrier).
+// (Un-normed inputs are copied by the TMA unit, see gemv_phase.)  K <= 2048.
+__device__ __forceinline__ void stage_columns(const bf16* __restrict__ src, int src_ld, float eps, bf16* __restrict__ save, int K,
+                                              int nc, char* __restrict__ xs, int xstride, const uint4* __restrict__ nw_s) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = K >> 3;
 #pragma unroll 1
   for (int col = warp; col < nc; col += NWARPS) {
     const uint4* xr = reinterpret_cast<const uint4*>(src + (size_t)col * src_ld);
     uint4* drow = reinterpret_cast<uint4*>(xs + (size_t)col * xstride);
-#pragma unroll 1
-    for (int vb = 0; vb < nv; vb += 256) {  // warp-uniform trip count (warp_sum below); one pass when K <= 2048
-      const int v0 = vb + lane;
-      uint4 v[8];
+    uint4 v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (v0 + 32 * i < nv) v[i] = ldcg16(xr + v0 + 32 * i);
-      if (normed) {
-        float ss = 0.f;
+    for (int i = 0; i < 8; ++i)
+      if (lane + 32 * i < nv) v[i] = ldcg16(xr + lane + 32 * i);
+    float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (v0 + 32 * i < nv) {
-            float f;
-            f = bf16lo(v[i].x); ss += f * f; f = bf16hi(v[i].x); ss += f * f;
-            f = bf16lo(v[i].y); ss += f * f; f = bf16hi(v[i].y); ss += f * f;
-            f = bf16lo(v[i].z); ss += f * f; f = bf16hi(v[i].z); ss += f * f;
-            f = bf16lo(v[i].w); ss += f * f; f = bf16hi(v[i].w); ss += f * f;
-          }
-        }
-        ss = warp_sum(ss);
-        const float inv = rsqrtf(ss / (float)K + eps);
+    for (int i = 0; i < 8; ++i) {
+      if (lane + 32 * i < nv) {
+        const uint32_t w4[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (v0 + 32 * i < nv) {
-            // bf16(bf16(x*inv) * w): fp32 scale, one packed RN conversion, then a packed bf16 multiply (HMUL2.BF16
-            // rounds the exact product to nearest-even = the reference's bf16 x bf16 -> bf16 multiply)
-            const uint4 w = nw_s[v0 + 32 * i];
-            uint4 o;
-            o.x = norm_pair(v[i].x, w.x, inv);
-            o.y = norm_pair(v[i].y, w.y, inv);
-            o.z = norm_pair(v[i].z, w.z, inv);
-            o.w = norm_pair(v[i].w, w.w, inv);
-            v[i] = o;
-            if (save) reinterpret_cast<uint4*>(save + (size_t)col * K)[v0 + 32 * i] = o;
-          }
-        }
+        for (int q = 0; q < 4; ++q) { const float lo = bf16lo(w4[q]), hi = bf16hi(w4[q]); ss += lo * lo; ss += hi * hi; }
       }
+    }
+    ss = warp_sum(ss);
+    const float inv = rsqrtf(ss / (float)K + eps);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (v0 + 32 * i < nv) drow[v0 + 32 * i] = v[i];
+    for (int i = 0; i < 8; ++i) {
+      if (lane + 32 * i < nv) {
+        // bf16(bf16(x*inv) * w): fp32 scale, one packed RN conversion, then a packed bf16 multiply (HMUL2.BF16
+        // rounds the exact product to nearest-even = the reference's bf16 x bf16 -> bf16 multiply)
+        const uint4 w = nw_s[lane + 32 * i];
+        uint4 o;
+        o.x = norm_pair(v[i].x, w.x, inv);
+        o.y = norm_pair(v[i].y, w.y, inv);
+        o.z = norm_pair(v[i].z, w.z, inv);
+        o.w = norm_pair(v[i].w, w.w, inv);
+        if (save) reinterpret_cast<uint4*>(save + (size_t)col * K)[lane + 32 * i] = o;
+        drow[lane + 32 * i] = o;
+      }
     }
   }
 }
@@ -311,40 +299,36 @@ __device__ __forceinline__ int idiv_small(int a, int b) {  // exact for 0 <= a <
   return __float2int_rz(__fdividef((float)a + 0.5f, (float)b));
 }
 
-// One full ring piece (4 k32-blocks of one tile) against the staged activations: all fragment loads first, then the
-// MMAs.  A block is two 512-byte halves; lane l's 16 bytes of a half ARE the four A registers of one m16n8k16 MMA
+// One full ring piece (4 k32-blocks of one tile): A fragments from the ring slot, B fragments already in registers.
+// A block is two 512-byte halves; lane l's 16 bytes of a half ARE the four A registers of one m16n8k16 MMA
 // (pack_weight_kernel), so no register shuffling sits between the loads and the tensor pipe.
-template <int NT, int NACC, int NCT>
-__device__ __forceinline__ void piece4(float (&acc)[NACC][NT][4], uint32_t sp, uint32_t xb, int xstride) {
-  uint4 a1[4], a2[4], b[4][NCT];
+template <int NT, int NACC>
+__device__ __forceinline__ void piece4(float (&acc)[NACC][NT][4], uint32_t sp, const uint4 (&b)[4][NT], int nct) {
+  uint4 a1[4], a2[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) { a1[i] = lds128(sp + i * 1024); a2[i] = lds128(sp + i * 1024 + 512); }
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int n = 0; n < NCT; ++n) b[i][n] = lds128(xb + (uint32_t)(i * 64 + n * 8 * xstride));
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int n = 0; n < NCT; ++n) {
-      mma_bf16_16816(acc[(2 * i) % NACC][n], a1[i].x, a1[i].y, a1[i].z, a1[i].w, b[i][n].x, b[i][n].y);
-      mma_bf16_16816(acc[(2 * i + 1) % NACC][n], a2[i].x, a2[i].y, a2[i].z, a2[i].w, b[i][n].z, b[i][n].w);
-    }
+    for (int n = 0; n < NT; ++n)
+      if (n < nct) {
+        mma_bf16_16816(acc[(2 * i) % NACC][n], a1[i].x, a1[i].y, a1[i].z, a1[i].w, b[i][n].x, b[i][n].y);
+        mma_bf16_16816(acc[(2 * i + 1) % NACC][n], a2[i].x, a2[i].y, a2[i].z, a2[i].w, b[i][n].z, b[i][n].w);
+      }
 }
 
-// B fragments of `count` (<= 4) consecutive k-blocks starting at block kb0 (wrapping at KB) straight from global memory
+// B fragments of 4 consecutive k-blocks starting at block kb0 (wrapping at KB) straight from global memory.
+// gsrc points at this lane's column g / k offset t*8; `rows_left` = nc - g (columns n*8+g beyond it read zero).
 template <int NT>
-__device__ __forceinline__ void load_bfrags(uint4 (&dst)[4][NT], const bf16* __restrict__ src, int src_ld, int nc, int nct, int kb0,
-                                            int KB, int count, int g, int t) {
+__device__ __forceinline__ void load_bfrags(uint4 (&dst)[4][NT], const bf16* __restrict__ gsrc, int src_ld, int rows_left, int nct,
+                                            int kb0, int KB) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int kk = kb0 + i;
-    while (kk >= KB) kk -= KB;
+    if (kk >= KB) kk -= KB;
 #pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      const int col = n * 8 + g;
-      dst[i][n] = (i < count && n < nct && col < nc) ? ldcg16(src + (size_t)col * src_ld + kk * 32 + t * 8) : make_uint4(0, 0, 0, 0);
-    }
+    for (int n = 0; n < NT; ++n)
+      dst[i][n] = (n < nct && n * 8 < rows_left) ? ldcg16(gsrc + (size_t)(n * 8) * src_ld + kk * 32) : make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -397,8 +381,8 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
 
   // ---- activations -> shared memory
   if (staged && (ntc > 0 || save)) {
-    if (normed || (P.flags & 2)) {
-      stage_columns(src, src_ld, normed, ph.eps, save, K, nc, xs, xstride, nw_s);
+    if (normed) {
+      stage_columns(src, src_ld, ph.eps, save, K, nc, xs, xstride, nw_s);
     } else {
       // plain copy of nc contiguous rows: one bulk (TMA) copy per column, completion on the CTA's x barrier
       if (tid == 0) {
@@ -470,73 +454,64 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
       int seg = 0;
       float* pp = part + ((warp * 2) * (NT * 8)) * PCOL;
       const uint32_t xb0 = xs_sh + (uint32_t)(g * xstride + t * 16);  // this lane's B-fragment base (column g of n-tile 0)
-      // B fragments of an un-staged input (K too large for the x area) come straight from L2, one piece AHEAD of the
-      // MMAs that use them (double buffer in registers): only the first piece of a run exposes the L2 latency
-      uint4 bq[4][NT];
-      if (!staged) load_bfrags<NT>(bq, src, src_ld, nc, nct, kbi, KB, q3ring::imin(rg.SB, rgm.u1 - u), g, t);
+      // Un-staged inputs (K too large for the x area: the down projections): B fragments come straight from L2 into
+      // registers, one piece AHEAD of the MMAs that use them, so only the first piece of a run exposes the L2 latency
+      const bf16* gsrc = src + (size_t)g * src_ld + t * 8;
+      uint4 bq[4][NT], bnx[4][NT];
+      if (!staged) load_bfrags<NT>(bq, gsrc, src_ld, nc - g, nct, kbi, KB);
 #pragma unroll 1
       while (u < rgm.u1) {
         const int nb = q3ring::imin(rg.SB, rgm.u1 - u);
-        uint4 bnx[4][NT];
+        const bool full = nb == 4 && kbi + 4 <= KB;  // every shipped shape: runs and tiles are multiples of 4 blocks
         if (!staged && u + nb < rgm.u1) {
           int kn = kbi + nb;
-          while (kn >= KB) kn -= KB;
-          load_bfrags<NT>(bnx, src, src_ld, nc, nct, kn, KB, q3ring::imin(rg.SB, rgm.u1 - u - nb), g, t);
+          if (kn >= KB) kn -= KB;
+          load_bfrags<NT>(bnx, gsrc, src_ld, nc - g, nct, kn, KB);
         }
         long long w0 = 0;
         if (g_prof_row) w0 = clock64();
         mbar_wait(rg.full + 8u * rg.c_slot, (uint32_t)rg.c_par, P.st);
         if (g_prof_row && tid == 0) wait_cycles += clock64() - w0;
         const uint32_t sp = rg.slots + (uint32_t)(rg.c_slot * rg.SB) * 1024u + (uint32_t)lane * 16u;
-        if (staged && nb == 4 && kbi + 4 <= KB) {
-          // fast path (every shipped shape: runs and tiles are multiples of 4 blocks): a full piece inside one tile.
-          // 8 A loads + the B loads are issued back to back, then 8 MMAs per n-tile on 4 independent accumulators
-          const uint32_t xb = xb0 + (uint32_t)kbi * 64u;
-          if (nct == 1) piece4<NT, NACC, 1>(acc, sp, xb, xstride);
-          else if (nct == 2) piece4<NT, NACC, (NT >= 2 ? 2 : 1)>(acc, sp, xb, xstride);
-          else piece4<NT, NACC, NT>(acc, sp, xb, xstride);
-          kbi += 4;
-          if (kbi == KB) {
-            flush_acc<NT, NACC>(acc, pp + seg * (NT * 8) * PCOL, nct, t, g);
-            kbi = 0;
-            ++seg;
-          }
-        } else {
-          // general path: partial pieces, a tile boundary inside the piece, un-staged inputs
-          uint4 am1[4], am2[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i < nb) { am1[i] = lds128(sp + i * 1024); am2[i] = lds128(sp + i * 1024 + 512); }
-          }
+        if (full) {
+          // a full piece inside one tile: all fragment loads are issued back to back, then 8 MMAs per n-tile on
+          // independent accumulators
           if (staged) {
+            const uint32_t xb = xb0 + (uint32_t)kbi * 64u;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (i < nb) {
-                int kk = kbi + i;
-                while (kk >= KB) kk -= KB;
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int n = 0; n < NT; ++n)
-                  if (n < nct) bq[i][n] = lds128(xb0 + (uint32_t)(n * 8 * xstride + kk * 64));
+              for (int n = 0; n < NT; ++n)
+                if (n < nct) bq[i][n] = lds128(xb + (uint32_t)(i * 64 + n * 8 * xstride));
+          }
+          piece4<NT, NACC>(acc, sp, bq, nct);
+          kbi += 4;
+        } else {
+          // general path (tiny test shapes, a tile boundary inside the piece): one block at a time, rolled
+#pragma unroll 1
+          for (int i = 0; i < nb; ++i) {
+            const uint4 a1 = lds128(sp + i * 1024), a2 = lds128(sp + i * 1024 + 512);
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+              if (n < nct) {
+                uint4 bb;
+                if (staged) bb = lds128(xb0 + (uint32_t)(n * 8 * xstride + kbi * 64));
+                else bb = (n * 8 + g < nc) ? ldcg16(gsrc + (size_t)(n * 8) * src_ld + kbi * 32) : make_uint4(0, 0, 0, 0);
+                mma_bf16_16816(acc[0][n], a1.x, a1.y, a1.z, a1.w, bb.x, bb.y);
+                mma_bf16_16816(acc[1][n], a2.x, a2.y, a2.z, a2.w, bb.z, bb.w);
               }
             }
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i < nb) {
-#pragma unroll
-              for (int n = 0; n < NT; ++n) {
-                if (n < nct) {
-                  mma_bf16_16816(acc[(2 * i) % NACC][n], am1[i].x, am1[i].y, am1[i].z, am1[i].w, bq[i][n].x, bq[i][n].y);
-                  mma_bf16_16816(acc[(2 * i + 1) % NACC][n], am2[i].x, am2[i].y, am2[i].z, am2[i].w, bq[i][n].z, bq[i][n].w);
-                }
-              }
-              if (++kbi == KB) {  // tile boundary inside the run: spill this tile's partial sums
-                flush_acc<NT, NACC>(acc, pp + seg * (NT * 8) * PCOL, nct, t, g);
-                kbi = 0;
-                ++seg;
-              }
+            if (++kbi == KB && i + 1 < nb) {  // tile boundary inside the piece
+              flush_acc<NT, NACC>(acc, pp + seg * (NT * 8) * PCOL, nct, t, g);
+              kbi = 0;
+              ++seg;
             }
           }
+        }
+        if (kbi == KB) {  // tile finished with this piece: spill its partial sums
+          flush_acc<NT, NACC>(acc, pp + seg * (NT * 8) * PCOL, nct, t, g);
+          kbi = 0;
+          ++seg;
         }
         ring_release(rg, lane);
         if (!staged) {

@@ -103,6 +103,7 @@ struct KParams {
   int G, eos, has_proj;
   int B;                    // sequences in this request (constant per launch)
   int len0[MAXB];           // prompt lengths
+  int max_len0;             // longest prompt of the batch (attention split count)
   int trailing_len[MAXB];
   q3_sampling sp;
   // sampler / embed resources

@@ -246,10 +246,14 @@ def _full_shape_case(model, lens, N, seed):
         tot += o.size
         same += int((o == r).sum())
         rows_equal += int((o == r).all())
-        if not (o == r).all():  # first divergence must sit on a near-tie of the oracle
+        if not (o == r).all():  # first divergence must sit on a near-tie of the oracle's PROCESSED scores
             f, gidx = np.argwhere(o != r)[0]
             lg = ref.record["talker_logits"][f][b] if gidx == 0 else ref.record["cp_logits"][f * (G - 1) + gidx - 1][b]
-            s = np.sort(lg)
+            sc = lg
+            if gidx == 0:  # codebook 0 goes through the talker's processors (suppress range, min-new-tokens, rep. penalty)
+                sc = OS.process_logits(lg, generated_ids=[int(x) for x in r[:f, 0]], **OT.talker_logits_processors(cfg, sp))
+                sc[cfg.codec_eos_token_id] = -np.inf  # suppress_eos
+            s = np.sort(sc[np.isfinite(sc)])
             assert s[-1] - s[-2] < 0.4 * float(np.std(lg)), (model, B, b, f, gidx, s[-1] - s[-2])
     Hh.report_parity(f"full_shape_{model}_B{B}", {"model": model, "batch": B, "frames": N, "ctx_max": max(lens) + N,
                                                   "worst_logit_err_over_std": worst, "free_running_code_match": same / tot,

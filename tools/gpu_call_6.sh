@@ -12,4 +12,4 @@ except Exception as e:
     print("bench failed", e); print(open("gpurun_out/bench_d.err").read()[-1500:])
 PY
 timeout 200 python tools/critical_path.py --batch 8 > gpurun_out/critical_b8.txt 2>&1; tail -14 gpurun_out/critical_b8.txt
-timeout 300 python tools/diag_free_run.py 32 > gpurun_out/diag32.txt 2>&1; tail -30 gpurun_out/diag32.txt
+timeout 300 python tools/critical_path.py --batch 1 > gpurun_out/critical_b1.txt 2>&1; tail -3 gpurun_out/critical_b1.txt
