@@ -484,7 +484,7 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
               for (int n = 0; n < NT; ++n)
                 if (n < nct) bq[i][n] = lds128(xb + (uint32_t)(i * 64 + n * 8 * xstride));
           }
-          piece4<NT, NACC>(acc, sp, bq, nct);
+          if (!(P.flags & 16)) piece4<NT, NACC>(acc, sp, bq, nct);  // (flag 16: experiment, skip the tensor work)
           kbi += 4;
         } else {
           // general path (tiny test shapes, a tile boundary inside the piece): one block at a time, rolled
