@@ -399,7 +399,7 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
   const uint32_t xs_sh = smem_addr(xs);
 
   // ---- activations -> shared memory
-  if (staged && (ntc > 0 || save)) {
+  if (staged && (ntc > 0 || save) && !(P.flags & 32)) {
     if (normed) {
       stage_columns(src, src_ld, ph.eps, save, K, nc, xs, xstride, nw_s);
     } else {
@@ -492,7 +492,10 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
         mbar_wait(rg.full + 8u * rg.c_slot, (uint32_t)rg.c_par, P.st);
         if (g_prof_row && tid == 0) wait_cycles += clock64() - w0;
         const uint32_t sp = rg.slots + (uint32_t)(rg.c_slot * rg.SB) * 1024u + (uint32_t)lane * 16u;
-        if (full) {
+        if (P.flags & 64) {
+          kbi += nb;  // (experiment: consume the ring without touching the data)
+          if (kbi > KB) kbi -= KB;
+        } else if (full) {
           // a full piece inside one tile: all fragment loads are issued back to back, then 8 MMAs per n-tile on
           // independent accumulators
           if (staged) {
@@ -551,7 +554,7 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
     PROF_MARK(3);
     // ---- cross-warp reduce + epilogue, one output element per thread-iteration
 #pragma unroll 1
-    for (int e = tid, it = 0; e < nelem; e += NTHREADS, ++it) {
+    for (int e = tid, it = 0; e < ((P.flags & 128) ? 0 : nelem); e += NTHREADS, ++it) {
       const int r = e & ((1 << rsh) - 1);
       const int tl = (e >> rsh) & ((1 << tbl) - 1);
       const int col = e >> (rsh + tbl);

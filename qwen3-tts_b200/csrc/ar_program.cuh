@@ -126,7 +126,7 @@ struct KParams {
   int n_forced;
   float* dbg_tlogits;
   float* dbg_clogits;
-  int flags;                // A/B knobs (Q3_FLAGS): 1 flag barrier instead of the counter, 2 LDG staging of un-normed inputs instead of TMA, 4 weight copies without L2 policies, 8 ring refills after the main loop instead of inside it
+  int flags;                // A/B knobs (Q3_FLAGS): 1 flag barrier instead of the counter, 2 LDG staging of un-normed inputs instead of TMA, 4 weight copies without L2 policies, 16 / 32 / 64 / 128 ablation (tools/phase_ablation.py): skip the tensor work / the staging / the main-loop work / the epilogue
   SmemPlan plan;
   float keep_fraction;      // share of the code predictor's weight lines fetched with L2 evict_last priority
   int cp_phases;            // phases [0, cp_phases) of the frame program belong to the code predictor
