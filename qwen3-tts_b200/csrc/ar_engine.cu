@@ -55,22 +55,18 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) q3_step_kernel(const __grid_co
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ Phase s_ph[2];
   __shared__ RoundTab s_tab;
-  __shared__ int s_stop;
-  __shared__ int s_issued[NWARPS];
   DevState* st = P.st;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool use_counter = (P.flags & 1) == 0;
   unsigned int epoch = 0;  // host resets bar_count / bar_flags to 0 before every launch
   PMeta* meta = reinterpret_cast<PMeta*>(smem + P.plan.meta_off);
   const int R = P.plan.nslots, SB = P.plan.slot_blocks;
-  const uint32_t full0 = smem_addr(smem + P.plan.bar_off);      // [NWARPS][R] full, [NWARPS][R] empty, then the x barrier
-  const uint32_t empty0 = full0 + 8u * (NWARPS * R);
-  const uint32_t xbar = empty0 + 8u * (NWARPS * R);
-  const uint32_t ring0 = smem_addr(smem + P.plan.ring_off);
+  const uint32_t full0 = smem_addr(smem + P.plan.bar_off);      // [NWARPS][R] full barriers, then the x barrier
+  const uint32_t xbar = full0 + 8u * (NWARPS * R);
   uint32_t xpar = 0;
   const int niter = P.mode == 1 ? P.max_iters : 1;
 
-  // ---- per-CTA phase metas: which contiguous weight bytes this CTA consumes in every phase
+  // ---- per-CTA phase metas: how many tiles of every phase this CTA owns
 #pragma unroll 1
   for (int i = tid; i < P.n_phases; i += CTA_THREADS) {
     const Phase* gp = P.prog + i;
@@ -81,114 +77,108 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) q3_step_kernel(const __grid_co
       q3ring::cta_tiles(gp->tq, gp->tr, (int)blockIdx.x, t0, ntc);
       m.ntc = (uint16_t)ntc;
       m.kb = (uint16_t)gp->kb;
-      m.woff16 = (uint32_t)(((reinterpret_cast<const char*>(gp->w) - P.wbase) + (size_t)t0 * gp->kb * 1024) >> 4);
     }
     meta[i] = m;
   }
   if (tid == 0) {
-    for (int i = 0; i < 2 * NWARPS * R + 1; ++i) mbar_init(full0 + 8u * i, 1);
+    for (int i = 0; i < NWARPS * R + 1; ++i) mbar_init(full0 + 8u * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");
     g_prof_row = nullptr;
-    s_stop = 0;
   }
-  if (tid < NWARPS) s_issued[tid] = -1;
   if (tid < (int)(sizeof(Phase) / 4))
     reinterpret_cast<uint32_t*>(&s_ph[0])[tid] = reinterpret_cast<const uint32_t*>(P.prog)[tid];
   __syncthreads();
+  if (s_ph[0].type == PH_GEMV && s_ph[0].norm_w != nullptr && tid < s_ph[0].kb * 4)
+    reinterpret_cast<uint4*>(smem + P.plan.nw_off)[tid] = reinterpret_cast<const uint4*>(s_ph[0].norm_w)[tid];
+  if (s_ph[0].type == PH_ATTN) attn_prefetch(s_ph[0], P, smem + P.plan.x_off, st->step);  // (synthetic profiling programs only)
 
-  if (warp >= NWARPS) {
-    // ================= producer warp: the TMA weight stream of all eight consumer rings =================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
-    if (warp == CTA_THREADS / 32 - 1) producer_loop(P, meta, niter, ring0, full0, empty0, &s_stop, s_issued, P.mode == 1 ? P.cp_phases : 0);
-  } else {
-    // ================= 8 consumer warps: the phase program =================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;" ::: "memory");
-    if (s_ph[0].type == PH_GEMV && s_ph[0].norm_w != nullptr && tid < s_ph[0].kb * 4)
-      reinterpret_cast<uint4*>(smem + P.plan.nw_off)[tid] = reinterpret_cast<const uint4*>(s_ph[0].norm_w)[tid];
-    if (s_ph[0].type == PH_ATTN) attn_prefetch(s_ph[0], P, smem + P.plan.x_off, st->step);  // (synthetic profiling programs only)
-    Ring rg;
-    rg.SB = SB; rg.R = R;
-    rg.slots = ring0 + (uint32_t)(warp * R * SB) * 1024u;
-    rg.full = full0 + 8u * (warp * R);
-    rg.empty = empty0 + 8u * (warp * R);
-    rg.c_slot = 0; rg.c_par = 0; rg.consumed = 0;
-    cta_sync();
+  // L2 eviction priority of the weight stream: everything is read once per frame-step or is too large to stay
+  // (an evict_last fraction for the code predictor's layers made no measurable difference: profiles/r02_l2_policy_ab.txt)
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
 
-    const int step_base = st->step;
-    int iters_done = 0;
-    int slot = 0;
-#pragma unroll 1
-    for (int it = 0; it < niter; ++it) {
-      const int frame = step_base + it;
-      if (P.mode == 1) {
-        bool all = true;
-        for (int b = 0; b < P.B; ++b) all = all && (ldcgi(&st->finished[b]) != 0);
-        if (all) break;
-      }
-#pragma unroll 1
-      for (int pi = 0; pi < P.n_phases; ++pi) {
-        // descriptor of this phase sits in s_ph[slot] (fetched one phase ahead).  The load of the NEXT descriptor is
-        // issued now into a register and only stored to smem after the body, so its L2 round trip is hidden.
-        int nx = pi + 1;
-        if (nx >= P.n_phases) nx = (P.mode == 1) ? 0 : -1;
-        const bool dhave = nx >= 0 && tid < (int)(sizeof(Phase) / 4);
-        uint32_t dreg = 0;
-        if (dhave) dreg = reinterpret_cast<const uint32_t*>(P.prog + nx)[tid];
-        const Phase& ph = s_ph[slot];
-        if (tid == 0) {
-          g_prof_row = (P.prof && it == 0) ? P.prof + ((size_t)pi * gridDim.x + blockIdx.x) * 16 : nullptr;
-          PROF_MARK(6);
-        }
-        const int type = ph.type;
-        if (type == PH_GEMV) xpar = gemv_phase<NT>(ph, meta[pi], P, rg, smem, &s_tab, xbar, xpar);
-        else if (type == PH_ATTN) attn_phase(ph, P, smem + P.plan.x_off, frame);
-        else sample_phase(ph, P, smem + P.plan.x_off, frame, P.mode == 0);
-        if (dhave) reinterpret_cast<uint32_t*>(&s_ph[slot ^ 1])[tid] = dreg;
-        cta_sync();  // body done (global writes of every thread precede thread 0's release), next descriptor visible
-        PROF_MARK(0);
-        grid_arrive(st, epoch, use_counter);
-        // work that does not depend on the other CTAs, between arrive and wait: the next GEMV's RMSNorm weights
-        // (load now, store after the wait) and the KV rows the next attention phase will need
-        uint4 nwv = make_uint4(0, 0, 0, 0);
-        bool nw_have = false;
-        if (nx >= 0) {
-          const Phase& nph = s_ph[slot ^ 1];
-          if (nph.type == PH_GEMV && nph.norm_w != nullptr && tid < nph.kb * 4) {
-            nwv = reinterpret_cast<const uint4*>(nph.norm_w)[tid];
-            nw_have = true;
-          } else if (nph.type == PH_ATTN) {
-            attn_prefetch(nph, P, smem + P.plan.x_off, pi + 1 >= P.n_phases ? frame + 1 : frame);
-          }
-        }
-        grid_wait(st, epoch, use_counter);
-        slot ^= 1;
-        if (nw_have) reinterpret_cast<uint4*>(smem + P.plan.nw_off)[tid] = nwv;
-        cta_sync();
-        PROF_MARK(1);
-      }
-      ++iters_done;
-    }
-    // ---- shutdown: stop the producer, then drain what it had already requested (never leave with bulk copies in
-    // flight into this CTA's shared memory)
-    if (tid == 0) s_stop = 1;
-    cta_sync();
-    {
-      volatile int* vi = s_issued;
-      const long long t0 = clock64();
-      int issued;
-      while ((issued = vi[warp]) < 0) {
-        if (clock64() - t0 > 8000000000LL) { st->error = 80; __threadfence(); __trap(); }
-      }
-#pragma unroll 1
-      while (rg.consumed < issued) {
-        mbar_wait(rg.full + 8u * rg.c_slot, (uint32_t)rg.c_par, st);
-        ring_release(rg, lane);
-      }
-    }
-    if (P.mode == 1 && blockIdx.x == 0 && tid == 0) st->step = step_base + iters_done;
+  // ---- this warp's weight ring: start streaming before anything else happens
+  Ring rg;
+  rg.SB = SB; rg.R = R;
+  rg.slots = smem_addr(smem + P.plan.ring_off) + (uint32_t)(warp * R * SB) * 1024u;
+  rg.full = full0 + 8u * (warp * R);
+  rg.c_slot = 0; rg.c_par = 0; rg.p_slot = 0; rg.outstanding = 0;
+  {
+    const uint32_t o0 = P.piece_off[blockIdx.x * NWARPS + warp], o1 = P.piece_off[blockIdx.x * NWARPS + warp + 1];
+    rg.list = P.pieces + o0;
+    rg.len = (int)(o1 - o0);
+    rg.li = 0;
+    rg.left = (long long)rg.len * niter;
+    rg.d0 = ring_desc(rg, 0);
+    rg.d1 = ring_desc(rg, 1);
   }
+#pragma unroll 1
+  for (int i = 0; i < R; ++i) ring_issue(rg, P, lane, policy);
   __syncthreads();
+
+  const int step_base = st->step;
+  int iters_done = 0;
+  int slot = 0;
+#pragma unroll 1
+  for (int it = 0; it < niter; ++it) {
+    const int frame = step_base + it;
+    if (P.mode == 1) {
+      bool all = true;
+      for (int b = 0; b < P.B; ++b) all = all && (ldcgi(&st->finished[b]) != 0);
+      if (all) break;
+    }
+#pragma unroll 1
+    for (int pi = 0; pi < P.n_phases; ++pi) {
+      // descriptor of this phase sits in s_ph[slot] (fetched one phase ahead).  The load of the NEXT descriptor is
+      // issued now into a register and only stored to smem after the body, so its L2 round trip is hidden.
+      int nx = pi + 1;
+      if (nx >= P.n_phases) nx = (P.mode == 1) ? 0 : -1;
+      const bool dhave = nx >= 0 && tid < (int)(sizeof(Phase) / 4);
+      uint32_t dreg = 0;
+      if (dhave) dreg = reinterpret_cast<const uint32_t*>(P.prog + nx)[tid];
+      const Phase& ph = s_ph[slot];
+      if (tid == 0) {
+        g_prof_row = (P.prof && it == 0) ? P.prof + ((size_t)pi * gridDim.x + blockIdx.x) * 16 : nullptr;
+        PROF_MARK(6);
+      }
+      const int type = ph.type;
+      if (type == PH_GEMV) xpar = gemv_phase<NT>(ph, meta[pi], P, rg, smem, &s_tab, xbar, xpar, policy);
+      else if (type == PH_ATTN) attn_phase(ph, P, smem + P.plan.x_off, frame);
+      else sample_phase(ph, P, smem + P.plan.x_off, frame, P.mode == 0);
+      if (dhave) reinterpret_cast<uint32_t*>(&s_ph[slot ^ 1])[tid] = dreg;
+      cta_sync();  // body done (global writes of every thread precede thread 0's release), next descriptor visible
+      PROF_MARK(0);
+      grid_arrive(st, epoch, use_counter);
+      // work that does not depend on the other CTAs, between arrive and wait: the next GEMV's RMSNorm weights
+      // (load now, store after the wait) and the KV rows the next attention phase will need
+      uint4 nwv = make_uint4(0, 0, 0, 0);
+      bool nw_have = false;
+      if (nx >= 0) {
+        const Phase& nph = s_ph[slot ^ 1];
+        if (nph.type == PH_GEMV && nph.norm_w != nullptr && tid < nph.kb * 4) {
+          nwv = reinterpret_cast<const uint4*>(nph.norm_w)[tid];
+          nw_have = true;
+        } else if (nph.type == PH_ATTN) {
+          attn_prefetch(nph, P, smem + P.plan.x_off, pi + 1 >= P.n_phases ? frame + 1 : frame);
+        }
+      }
+      grid_wait(st, epoch, use_counter);
+      slot ^= 1;
+      if (nw_have) reinterpret_cast<uint4*>(smem + P.plan.nw_off)[tid] = nwv;
+      cta_sync();
+      PROF_MARK(1);
+    }
+    ++iters_done;
+  }
+  // never leave with bulk copies in flight into this CTA's shared memory (early exit: every row finished)
+#pragma unroll 1
+  while (rg.outstanding > 0) {
+    mbar_wait(rg.full + 8u * rg.c_slot, (uint32_t)rg.c_par, st);
+    if (++rg.c_slot == rg.R) { rg.c_slot = 0; rg.c_par ^= 1; }
+    --rg.outstanding;
+  }
+  if (P.mode == 1 && blockIdx.x == 0 && tid == 0) st->step = step_base + iters_done;
 }
 
 }  // namespace
@@ -201,6 +191,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) q3_step_kernel(const __grid_co
 struct PackedW {
   uint4* w = nullptr;
   int n = 0, k = 0;
+};
+
+// device copy of a program's ring-piece table (see ar_gemv.cuh: weight rings)
+struct PieceTable {
+  uint32_t* pieces = nullptr;
+  uint32_t* off = nullptr;
+  size_t n_pieces = 0;
 };
 
 struct q3_engine {
@@ -236,6 +233,7 @@ struct q3_engine {
   int cp_phases = 0;
   int nt_frame = 1, nt_head = 1, max_dyn_smem = 0;
   SmemPlan plan_frame{}, plan_head{};
+  PieceTable pt_frame{}, pt_head{};
   bool use_proj_tab = true;   // Q3_CP_PROJ_TAB=0 keeps the projection GEMV in passes >= 1 (A/B knob)
   bf16* proj_tab = nullptr;   // small_to_mtp_projection(cp.codec_embedding) [(G-1)*Vc][Hc], built once at finalize
   std::vector<Phase> prog_layers, prog_head, prog_frame;
@@ -441,6 +439,52 @@ static int add_layers(q3_engine* e, std::vector<Phase>& prog, const char* pfx, S
   return 0;
 }
 
+// Piece table of a program: for every (CTA, warp) the sequence of ring pieces (offset from the weight arena base in
+// 16-byte units | number of 1 KB blocks) of ONE pass over the program, enumerated with the same iterator the model
+// check in tests/test_ring_model.py exercises.  The kernel's consumer loop derives the same sizes from run_geom().
+static int build_piece_table(q3_engine* e, const std::vector<Phase>& prog, int SB, PieceTable* out) {
+  const int grid = e->sm_count, n = (int)prog.size();
+  std::vector<uint32_t> pieces, off;
+  off.reserve((size_t)grid * NWARPS + 1);
+  std::vector<q3ring::PMeta> meta(n);
+  for (int cta = 0; cta < grid; ++cta) {
+    for (int i = 0; i < n; ++i) {
+      q3ring::PMeta m{0, 0, 0};
+      if (prog[i].type == PH_GEMV) {
+        int t0, ntc;
+        q3ring::cta_tiles(prog[i].tq, prog[i].tr, cta, t0, ntc);
+        m.ntc = (uint16_t)ntc;
+        m.kb = (uint16_t)prog[i].kb;
+        const size_t byte_off = (size_t)(reinterpret_cast<const char*>(prog[i].w) - e->wbase) + (size_t)t0 * prog[i].kb * 1024;
+        Q3_REQUIRE((byte_off >> 4) < ((size_t)1 << 32) && (byte_off & 1023) == 0, "weight offset out of range / unaligned");
+        m.woff16 = (uint32_t)(byte_off >> 4);
+      }
+      meta[i] = m;
+    }
+    for (int warp = 0; warp < NWARPS; ++warp) {
+      off.push_back((uint32_t)pieces.size());
+      q3ring::ProdIter it;
+      q3ring::prod_init(it);
+      q3ring::prod_next_run(it, meta.data(), n, 1, warp);
+      while (!it.done) {
+        const int nb = q3ring::imin(SB, it.u1 - it.u);
+        pieces.push_back((uint32_t)(q3ring::prod_piece_offset(it) >> 4) | (uint32_t)nb);
+        it.u += nb;
+        if (it.u >= it.u1) q3ring::prod_next_run(it, meta.data(), n, 1, warp);
+      }
+    }
+  }
+  off.push_back((uint32_t)pieces.size());
+  e->release(out->pieces);
+  e->release(out->off);
+  out->pieces = nullptr; out->off = nullptr;
+  if (e->alloc(&out->pieces, pieces.size() + 8) || e->alloc(&out->off, off.size())) return 1;
+  out->n_pieces = pieces.size();
+  Q3_CUDA(cudaMemcpy(out->pieces, pieces.data(), pieces.size() * 4, cudaMemcpyHostToDevice));
+  Q3_CUDA(cudaMemcpy(out->off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
 // Shared-memory plan of one program at one batch class (layout: ar_program.cuh).  Marks every GEMV phase as staged
 // (activations copied to the x area once, B fragments read from shared memory) or not (B fragments straight from L2:
 // only inputs that do not fit, i.e. K = intermediate_size at B > 8).
@@ -462,7 +506,7 @@ static int make_smem_plan(q3_engine* e, std::vector<Phase>& prog, int B, int nt,
   pl.nw_off = pl.part_off + part_bytes_nt(nt);
   pl.ring_off = up(pl.nw_off + NW_BYTES, 1024);
   const int meta_bytes = up((int)prog.size() * (int)sizeof(q3ring::PMeta), 16);
-  const int bar_bytes = 8 * (2 * NWARPS * MAX_SLOTS + 1) + 8;  // full + empty barrier per ring slot, the x barrier
+  const int bar_bytes = 8 * (NWARPS * MAX_SLOTS + 1) + 8;  // one full barrier per ring slot, the x barrier
   // batch classes 1-2 stay under the 196 KB carve-out (195 KB per CTA) so that 32 KB of the SM remain L1: the phase
   // functions' stack traffic then hits L1 instead of making an L2 round trip each (Q3_SMEM_FULL=1 lifts the cap: A/B)
   int limit = e->max_dyn_smem;
@@ -567,6 +611,9 @@ static int build_programs(q3_engine* e, int B) {
   if (make_smem_plan(e, e->prog_head, B, e->nt_head, &e->plan_head) || make_smem_plan(e, e->prog_frame, B, e->nt_frame, &e->plan_frame))
     return 1;
   Q3_REQUIRE((int)F.size() <= MAX_PHASES, "frame program has %d phases (max %d)", (int)F.size(), MAX_PHASES);
+  if (build_piece_table(e, e->prog_head, e->plan_head.slot_blocks, &e->pt_head) ||
+      build_piece_table(e, e->prog_frame, e->plan_frame.slot_blocks, &e->pt_frame))
+    return 1;
   // upload (a batch-size change is rare: wait for launches that may still walk the old program)
   Q3_CUDA(cudaDeviceSynchronize());
   const size_t total = e->prog_layers.size() + e->prog_head.size() + F.size();
@@ -668,7 +715,7 @@ extern "C" int q3_engine_finalize(q3_engine* e) {
 }
 
 static int launch_program(q3_engine* e, int off, int n, int mode, int max_iters, int nt, const SmemPlan& plan,
-                          int* codes_dev, cudaStream_t stream) {
+                          const PieceTable& pt, int* codes_dev, cudaStream_t stream) {
   KParams P{};
   P.prog = e->prog_dev + off; P.n_phases = n; P.mode = mode; P.max_iters = max_iters; P.st = e->st;
   P.talker = e->talker; P.cp = e->cp; P.G = e->cfg.num_code_groups; P.eos = e->cfg.codec_eos_token_id;
@@ -683,6 +730,7 @@ static int launch_program(q3_engine* e, int off, int n, int mode, int max_iters,
   P.tts_pad = e->tts_pad; P.seen = e->seen; P.codes_out = codes_dev; P.codes_stride = e->codes_stride;
   P.split_buf = e->split_buf; P.forced = e->forced; P.n_forced = e->n_forced; P.dbg_tlogits = e->dbg_t; P.dbg_clogits = e->dbg_c; P.prof = (mode == 1) ? e->prof : nullptr;
   P.flags = e->flags; P.wbase = e->wbase; P.keep_fraction = e->keep_fraction;
+  P.pieces = pt.pieces; P.piece_off = pt.off;
   P.plan = plan; P.cp_phases = (off == e->off_frame && n == (int)e->prog_frame.size()) ? e->cp_phases : 0;
   Q3_REQUIRE(n <= MAX_PHASES, "program of %d phases exceeds %d", n, MAX_PHASES);
   Q3_CUDA(cudaMemsetAsync(&e->st->bar_count, 0, sizeof(unsigned int) * (1 + 256), stream));  // counter + per-CTA flags
@@ -783,7 +831,7 @@ extern "C" int q3_prefill(q3_engine* e, int32_t B, const void* embeds_dev, const
   Q3_CUDA(cudaGetLastError());
   pf_gather_last_kernel<<<B, 128, 0, stream>>>(pl, e->pf_x, e->h_last, H);
   // head + sample codebook-0 of frame 0 (codes are materialised by q3_decode's first call via st->c0)
-  if (launch_program(e, e->off_head, (int)e->prog_head.size(), 0, 1, e->nt_head, e->plan_head, nullptr, stream)) return 1;
+  if (launch_program(e, e->off_head, (int)e->prog_head.size(), 0, 1, e->nt_head, e->plan_head, e->pt_head, nullptr, stream)) return 1;
   return 0;
 }
 
@@ -796,7 +844,7 @@ extern "C" int q3_decode(q3_engine* e, int32_t max_frames, int32_t* codes_dev, i
   Q3_REQUIRE(e->max_len0 + e->frames_issued + max_frames <= e->cfg.max_ctx, "KV capacity exceeded: prompt %d + %d frames > max_ctx %d",
              e->max_len0, e->frames_issued + max_frames, e->cfg.max_ctx);
   e->frames_issued += max_frames;
-  return launch_program(e, e->off_frame, (int)e->prog_frame.size(), 1, max_frames, e->nt_frame, e->plan_frame, codes_dev, stream);
+  return launch_program(e, e->off_frame, (int)e->prog_frame.size(), 1, max_frames, e->nt_frame, e->plan_frame, e->pt_frame, codes_dev, stream);
 }
 
 extern "C" int q3_get_progress(q3_engine* e, int32_t* frames_done, int32_t* n_valid, int32_t* finished) {
@@ -869,18 +917,22 @@ extern "C" int q3_debug_time_phases(q3_engine* e, int32_t first, int32_t span, i
   e->prog_dev = dev;
   const int nt = e->nt_frame;
   SmemPlan plan;
+  PieceTable pt;
   int rc = make_smem_plan(e, prog, e->B, nt, &plan);
+  if (!rc) rc = build_piece_table(e, prog, plan.slot_blocks, &pt);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  if (!rc) rc = launch_program(e, 0, n, 0, 1, nt, plan, nullptr, stream);  // warm
+  if (!rc) rc = launch_program(e, 0, n, 0, 1, nt, plan, pt, nullptr, stream);  // warm
   cudaEventRecord(e0, stream);
-  if (!rc) rc = launch_program(e, 0, n, 0, 1, nt, plan, nullptr, stream);
+  if (!rc) rc = launch_program(e, 0, n, 0, 1, nt, plan, pt, nullptr, stream);
   cudaEventRecord(e1, stream);
   cudaStreamSynchronize(stream);
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
   if (ms_out) *ms_out = ms;
   e->prog_dev = saved;
+  e->release(pt.pieces);
+  e->release(pt.off);
   cudaFree(dev);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return rc;

@@ -70,8 +70,8 @@ __device__ __forceinline__ void grid_wait(DevState* st, unsigned int epoch, bool
   }
 }
 
-// barrier of the 256 worker threads (named barrier 1): the producer warp never takes part in phase-level syncs
-__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// CTA-wide barrier of the phase code
+__device__ __forceinline__ void cta_sync() { __syncthreads(); }
 
 // fine-grained profiling marks (thread 0 only, first frame of a profiled launch)
 __shared__ unsigned long long* g_prof_row;
@@ -139,84 +139,61 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight rings.  Every consumer warp owns a private ring of R slots (SB KB each) in shared memory; ONE producer
-// warp feeds all eight: its lane w walks consumer warp w's deterministic piece sequence (ar_ring.cuh) and issues
-// one cp.async.bulk per piece as soon as the slot is free (empty mbarrier, armed by the consumer) — across phases
-// and grid barriers, so weight streaming never waits for the activations' dependency chain and none of the
-// producer's address arithmetic sits on the consumers' critical path (measured: ~0.3 us per piece when the consumer
-// warps produced for themselves, profiles/r02_phase_breakdown.txt).
+// weight rings.  Every warp owns a private ring of R slots (SB KB each) in shared memory and is its own TMA producer:
+// when it has consumed a slot its lane 0 immediately refills it with the piece R positions ahead in the warp's
+// deterministic piece sequence — across phases and grid barriers, so weight streaming never waits for the activations'
+// dependency chain.  The sequence itself (address and size of every piece of one program pass, per CTA and warp) is
+// a TABLE built once on the host with the iterator of ar_ring.cuh (build_piece_table), so a refill costs one
+// descriptor word (loaded two refills ahead), one expect_tx and one cp.async.bulk: nothing to compute on the device.
+// (Measured alternatives, profiles/r02_phase_breakdown.txt: a device-side iterator inside the consumer loop cost
+// ~0.3 us per piece, a dedicated producer warp ~0.7 us per piece of serialised iterator work.)
 // ------------------------------------------------------------------------------------------------
-struct Ring {              // consumer-side view of one warp's ring
+struct Ring {
   uint32_t slots;          // shared address of the warp's first slot
-  uint32_t full, empty;    // shared addresses of its first full / empty mbarrier
+  uint32_t full;           // shared address of its first full mbarrier
   int SB, R;               // blocks per slot, slots
-  int c_slot, c_par;       // position / parity of the current lap
-  int consumed;            // pieces consumed so far
+  int c_slot, c_par;       // consumer position / parity of the current lap
+  int p_slot;              // next slot to fill
+  const uint32_t* list;    // this warp's piece list (one program pass)
+  int len;                 // pieces per pass
+  int li;                  // index in `list` of the next piece to request
+  long long left;          // pieces still to request in this launch
+  int outstanding;         // requested, not yet consumed
+  uint32_t d0, d1;         // descriptors of the next two requests (prefetched)
 };
 
-__device__ __forceinline__ void ring_release(Ring& rg, int lane) {
-  __syncwarp();
-  if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(rg.empty + 8u * rg.c_slot) : "memory");
-  if (++rg.c_slot == rg.R) { rg.c_slot = 0; rg.c_par ^= 1; }
-  ++rg.consumed;
+__device__ __forceinline__ uint32_t ring_desc(const Ring& rg, int ahead) {
+  if (rg.len == 0) return 0;
+  int i = rg.li + ahead;
+  while (i >= rg.len) i -= rg.len;
+  return __ldg(rg.list + i);
 }
 
-// the producer warp: lane w < NWARPS serves consumer warp w until its sequence ends or the workers say stop
-__device__ __forceinline__ void producer_loop(const KParams& P, const PMeta* meta, int niter, uint32_t ring0, uint32_t full0,
-                                              uint32_t empty0, volatile int* s_stop, volatile int* s_issued, int cp_phases) {
-  const int w = threadIdx.x & 31;
-  if (w >= NWARPS) return;
-  const int SB = P.plan.slot_blocks, R = P.plan.nslots;
-  uint64_t pol_keep, pol_stream;
-  asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol_keep) : "f"(P.keep_fraction));
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-  ProdIter it;
-  q3ring::prod_init(it);
-  q3ring::prod_next_run(it, meta, P.n_phases, niter, w);
-  const uint32_t slots = ring0 + (uint32_t)(w * R * SB) * 1024u, full = full0 + 8u * (w * R), empty = empty0 + 8u * (w * R);
-  int slot = 0, par = 1;  // a fresh mbarrier passes a wait on the "previous" phase: the first lap never blocks
-  int issued = 0;
-  // The eight lanes stay CONVERGED: every iteration each lane tests its own slot without blocking, the lanes whose
-  // slot is free issue their next piece, the others skip.  (A blocking try_wait per lane serialises the rings: the
-  // warp sits in one lane's suspended wait while the other seven rings starve — measured ~1.2 us per piece.)
-  long long t0 = clock64();  // time of the last issue (watchdog)
-  while (true) {
-    const bool active = !it.done;
-    if (!__any_sync(0x000000ffu, active)) break;
-    bool ready = false;
-    if (active) {
-      uint32_t ok;
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(ok)
-          : "r"(empty + 8u * slot), "r"((uint32_t)par)
-          : "memory");
-      ready = ok != 0;
-    }
-    if (ready) {
-      const int nb = q3ring::imin(SB, it.u1 - it.u);
-      const uint32_t bytes = (uint32_t)nb << 10;
-      const uint32_t bar = full + 8u * slot;
-      mbar_expect_tx(bar, bytes);
-      // phases [0, cp_phases) of the frame program are the code predictor: its layer weights are re-read 15x per frame
-      if (P.flags & 4) bulk_g2s_plain(slots + (uint32_t)(slot * SB) * 1024u, P.wbase + q3ring::prod_piece_offset(it), bytes, bar);
-      else bulk_g2s(slots + (uint32_t)(slot * SB) * 1024u, P.wbase + q3ring::prod_piece_offset(it), bytes, bar,
-                    it.pi < cp_phases ? pol_keep : pol_stream);
-      it.u += nb;
-      if (it.u >= it.u1) q3ring::prod_next_run(it, meta, P.n_phases, niter, w);
-      if (++slot == R) { slot = 0; par ^= 1; }
-      ++issued;
-      t0 = clock64();
-    }
-    if (!__any_sync(0x000000ffu, ready)) {  // every ring is full: back off, leave the issue slots to the consumers
-      if (*s_stop) break;
-      __nanosleep(64);
-      if (clock64() - t0 > 40000000000LL) { P.st->error = 79; __threadfence(); __trap(); }
-    }
+// request the next piece into slot p_slot (lane 0 issues; every lane keeps the bookkeeping)
+__device__ __forceinline__ void ring_issue(Ring& rg, const KParams& P, int lane, uint64_t policy) {
+  if (rg.left <= 0) return;
+  const uint32_t d = rg.d0;
+  if (lane == 0) {
+    const uint32_t bytes = (d & 7u) << 10;
+    const uint32_t bar = rg.full + 8u * rg.p_slot;
+    mbar_expect_tx(bar, bytes);
+    const char* src = P.wbase + ((size_t)(d & ~63u) << 4);
+    if (P.flags & 4) bulk_g2s_plain(rg.slots + (uint32_t)(rg.p_slot * rg.SB) * 1024u, src, bytes, bar);
+    else bulk_g2s(rg.slots + (uint32_t)(rg.p_slot * rg.SB) * 1024u, src, bytes, bar, policy);
   }
-  s_issued[w] = issued;  // the consumer drains [consumed, issued) before the CTA exits
+  if (++rg.p_slot == rg.R) rg.p_slot = 0;
+  if (++rg.li == rg.len) rg.li = 0;
+  --rg.left;
+  ++rg.outstanding;
+  rg.d0 = rg.d1;
+  rg.d1 = ring_desc(rg, 1);  // arrives long before it is needed (two refills ahead)
+}
+
+__device__ __forceinline__ void ring_release(Ring& rg, const KParams& P, int lane, uint64_t policy) {
+  __syncwarp();  // every lane's reads of the slot are done before the async proxy overwrites it
+  if (++rg.c_slot == rg.R) { rg.c_slot = 0; rg.c_par ^= 1; }
+  --rg.outstanding;
+  ring_issue(rg, P, lane, policy);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -377,7 +354,7 @@ __device__ __forceinline__ void flush_acc(float (&acc)[NACC][NT][4], float* pp, 
 // The phase body.  `m` is this CTA's meta of the phase (tiles owned, K blocks); the weights arrive through the ring.
 template <int NT>
 __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, const KParams& P, Ring& rg, unsigned char* smem,
-                                               RoundTab* tab, uint32_t xbar, uint32_t xpar) {
+                                               RoundTab* tab, uint32_t xbar, uint32_t xpar, uint64_t policy) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int KB = m.kb, K = KB * 32, epi = ph.epi, ntc = m.ntc;
@@ -535,7 +512,7 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
           kbi = 0;
           ++seg;
         }
-        ring_release(rg, lane);
+        ring_release(rg, P, lane, policy);
         if (!staged) {
 #pragma unroll
           for (int i = 0; i < 4; ++i)

@@ -7,7 +7,7 @@ namespace {
 
 constexpr int NTHREADS = 256;                 // worker threads (8 consumer warps)
 constexpr int NWARPS = NTHREADS / 32;
-constexpr int CTA_THREADS = NTHREADS + 128;    // + one producer warp that owns the TMA weight stream
+constexpr int CTA_THREADS = NTHREADS;
 constexpr int HD = 128;          // head_dim (required)
 constexpr int MAXB = Q3_MAX_BATCH;
 constexpr int MAXCOLS = 32;      // columns per pass (batch rows or prefill tokens)
@@ -130,7 +130,9 @@ struct KParams {
   SmemPlan plan;
   float keep_fraction;      // share of the code predictor's weight lines fetched with L2 evict_last priority
   int cp_phases;            // phases [0, cp_phases) of the frame program belong to the code predictor
-  const char* wbase;        // lowest address of the packed GEMV weights (PMeta offsets are relative to it)
+  const char* wbase;        // lowest address of the packed GEMV weights (piece offsets are relative to it)
+  const uint32_t* pieces;   // piece table of this program: per (CTA, warp) the (offset/16 | blocks) of every ring piece of ONE pass
+  const uint32_t* piece_off;  // [grid*NWARPS + 1] start of each (CTA, warp) list in `pieces`
   unsigned long long* prof;  // [n_phases][grid][16]: globaltimer ns [0] phase end, [1] barrier passed, [2..4] inner marks, [6] start, [7],[8] warp-0 marks; cycles [5],[9],[10]
 };
 
