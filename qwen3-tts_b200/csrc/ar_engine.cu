@@ -105,13 +105,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) q3_step_kernel(const __grid_co
   rg.full = full0 + 8u * (warp * R);
   rg.c_slot = 0; rg.c_par = 0; rg.p_slot = 0; rg.outstanding = 0;
   {
-    const uint32_t o0 = P.piece_off[blockIdx.x * NWARPS + warp], o1 = P.piece_off[blockIdx.x * NWARPS + warp + 1];
-    rg.list = P.pieces + o0;
-    rg.len = (int)(o1 - o0);
-    rg.li = 0;
-    rg.left = (long long)rg.len * niter;
-    rg.d0 = ring_desc(rg, 0);
-    rg.d1 = ring_desc(rg, 1);
+    const uint32_t o0 = P.run_off[blockIdx.x * NWARPS + warp], o1 = P.run_off[blockIdx.x * NWARPS + warp + 1];
+    ring_init(rg, P.runs + o0, (int)(o1 - o0), (long long)(o1 - o0) * niter);
   }
 #pragma unroll 1
   for (int i = 0; i < R; ++i) ring_issue(rg, P, lane, policy);
@@ -195,9 +190,9 @@ struct PackedW {
 
 // device copy of a program's ring-piece table (see ar_gemv.cuh: weight rings)
 struct PieceTable {
-  uint32_t* pieces = nullptr;
+  uint2* runs = nullptr;
   uint32_t* off = nullptr;
-  size_t n_pieces = 0;
+  size_t n_runs = 0;
 };
 
 struct q3_engine {
@@ -439,12 +434,14 @@ static int add_layers(q3_engine* e, std::vector<Phase>& prog, const char* pfx, S
   return 0;
 }
 
-// Piece table of a program: for every (CTA, warp) the sequence of ring pieces (offset from the weight arena base in
-// 16-byte units | number of 1 KB blocks) of ONE pass over the program, enumerated with the same iterator the model
-// check in tests/test_ring_model.py exercises.  The kernel's consumer loop derives the same sizes from run_geom().
+// Run table of a program: for every (CTA, warp) the sequence of contiguous weight runs (offset from the weight arena
+// base in 16-byte units, number of 1 KB blocks) of ONE pass over the program, enumerated with the same iterator the
+// model check in tests/test_ring_model.py exercises.  The kernel's consumer loop derives the same runs from run_geom().
 static int build_piece_table(q3_engine* e, const std::vector<Phase>& prog, int SB, PieceTable* out) {
   const int grid = e->sm_count, n = (int)prog.size();
-  std::vector<uint32_t> pieces, off;
+  (void)SB;
+  std::vector<uint2> pieces;
+  std::vector<uint32_t> off;
   off.reserve((size_t)grid * NWARPS + 1);
   std::vector<q3ring::PMeta> meta(n);
   for (int cta = 0; cta < grid; ++cta) {
@@ -467,20 +464,18 @@ static int build_piece_table(q3_engine* e, const std::vector<Phase>& prog, int S
       q3ring::prod_init(it);
       q3ring::prod_next_run(it, meta.data(), n, 1, warp);
       while (!it.done) {
-        const int nb = q3ring::imin(SB, it.u1 - it.u);
-        pieces.push_back((uint32_t)(q3ring::prod_piece_offset(it) >> 4) | (uint32_t)nb);
-        it.u += nb;
-        if (it.u >= it.u1) q3ring::prod_next_run(it, meta.data(), n, 1, warp);
+        pieces.push_back(make_uint2((uint32_t)(q3ring::prod_piece_offset(it) >> 4), (uint32_t)(it.u1 - it.u)));
+        q3ring::prod_next_run(it, meta.data(), n, 1, warp);
       }
     }
   }
   off.push_back((uint32_t)pieces.size());
-  e->release(out->pieces);
+  e->release(out->runs);
   e->release(out->off);
-  out->pieces = nullptr; out->off = nullptr;
-  if (e->alloc(&out->pieces, pieces.size() + 8) || e->alloc(&out->off, off.size())) return 1;
-  out->n_pieces = pieces.size();
-  Q3_CUDA(cudaMemcpy(out->pieces, pieces.data(), pieces.size() * 4, cudaMemcpyHostToDevice));
+  out->runs = nullptr; out->off = nullptr;
+  if (e->alloc(&out->runs, pieces.size() + 8) || e->alloc(&out->off, off.size())) return 1;
+  out->n_runs = pieces.size();
+  Q3_CUDA(cudaMemcpy(out->runs, pieces.data(), pieces.size() * sizeof(uint2), cudaMemcpyHostToDevice));
   Q3_CUDA(cudaMemcpy(out->off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
   return 0;
 }
@@ -730,7 +725,7 @@ static int launch_program(q3_engine* e, int off, int n, int mode, int max_iters,
   P.tts_pad = e->tts_pad; P.seen = e->seen; P.codes_out = codes_dev; P.codes_stride = e->codes_stride;
   P.split_buf = e->split_buf; P.forced = e->forced; P.n_forced = e->n_forced; P.dbg_tlogits = e->dbg_t; P.dbg_clogits = e->dbg_c; P.prof = (mode == 1) ? e->prof : nullptr;
   P.flags = e->flags; P.wbase = e->wbase; P.keep_fraction = e->keep_fraction;
-  P.pieces = pt.pieces; P.piece_off = pt.off;
+  P.runs = pt.runs; P.run_off = pt.off;
   P.plan = plan; P.cp_phases = (off == e->off_frame && n == (int)e->prog_frame.size()) ? e->cp_phases : 0;
   Q3_REQUIRE(n <= MAX_PHASES, "program of %d phases exceeds %d", n, MAX_PHASES);
   Q3_CUDA(cudaMemsetAsync(&e->st->bar_count, 0, sizeof(unsigned int) * (1 + 256), stream));  // counter + per-CTA flags
@@ -931,7 +926,7 @@ extern "C" int q3_debug_time_phases(q3_engine* e, int32_t first, int32_t span, i
   cudaEventElapsedTime(&ms, e0, e1);
   if (ms_out) *ms_out = ms;
   e->prog_dev = saved;
-  e->release(pt.pieces);
+  e->release(pt.runs);
   e->release(pt.off);
   cudaFree(dev);
   cudaEventDestroy(e0); cudaEventDestroy(e1);

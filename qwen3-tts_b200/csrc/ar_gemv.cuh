@@ -142,9 +142,10 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 // weight rings.  Every warp owns a private ring of R slots (SB KB each) in shared memory and is its own TMA producer:
 // when it has consumed a slot its lane 0 immediately refills it with the piece R positions ahead in the warp's
 // deterministic piece sequence — across phases and grid barriers, so weight streaming never waits for the activations'
-// dependency chain.  The sequence itself (address and size of every piece of one program pass, per CTA and warp) is
-// a TABLE built once on the host with the iterator of ar_ring.cuh (build_piece_table), so a refill costs one
-// descriptor word (loaded two refills ahead), one expect_tx and one cp.async.bulk: nothing to compute on the device.
+// dependency chain.  The sequence itself is a TABLE built once on the host with the iterator of ar_ring.cuh
+// (build_run_table): per CTA and warp the (address, length) of every contiguous run of one program pass; pieces are
+// the <= SB-block chunks of a run.  A refill costs one expect_tx and one cp.async.bulk; the next run's descriptor is
+// loaded a whole run ahead, so nothing is computed and no load latency is exposed on the device.
 // (Measured alternatives, profiles/r02_phase_breakdown.txt: a device-side iterator inside the consumer loop cost
 // ~0.3 us per piece, a dedicated producer warp ~0.7 us per piece of serialised iterator work.)
 // ------------------------------------------------------------------------------------------------
@@ -154,39 +155,44 @@ struct Ring {
   int SB, R;               // blocks per slot, slots
   int c_slot, c_par;       // consumer position / parity of the current lap
   int p_slot;              // next slot to fill
-  const uint32_t* list;    // this warp's piece list (one program pass)
-  int len;                 // pieces per pass
-  int li;                  // index in `list` of the next piece to request
-  long long left;          // pieces still to request in this launch
-  int outstanding;         // requested, not yet consumed
-  uint32_t d0, d1;         // descriptors of the next two requests (prefetched)
+  const uint2* list;       // this warp's RUN list of one program pass: (offset from the weight base / 16, 1 KB blocks)
+  int len;                 // runs per pass
+  int ri;                  // index in `list` of the run held in `nxt`
+  long long runs_left;     // runs of this launch not yet started (including the one in `nxt`)
+  uint32_t cur_off;        // current run: next block's offset / 16
+  int cur_left;            // blocks of the current run not yet requested
+  uint2 nxt;               // the following run (prefetched a whole run ahead: its L2 latency is never exposed)
+  int outstanding;         // pieces requested, not yet consumed
 };
 
-__device__ __forceinline__ uint32_t ring_desc(const Ring& rg, int ahead) {
-  if (rg.len == 0) return 0;
-  int i = rg.li + ahead;
-  while (i >= rg.len) i -= rg.len;
-  return __ldg(rg.list + i);
+__device__ __forceinline__ void ring_init(Ring& rg, const uint2* list, int len, long long total_runs) {
+  rg.list = list; rg.len = len; rg.ri = 0; rg.runs_left = total_runs;
+  rg.cur_off = 0; rg.cur_left = 0;
+  rg.nxt = len > 0 ? __ldg(list) : make_uint2(0, 0);
 }
 
-// request the next piece into slot p_slot (lane 0 issues; every lane keeps the bookkeeping)
+// request the next piece (<= SB blocks of the current run) into slot p_slot; lane 0 issues, every lane keeps the books
 __device__ __forceinline__ void ring_issue(Ring& rg, const KParams& P, int lane, uint64_t policy) {
-  if (rg.left <= 0) return;
-  const uint32_t d = rg.d0;
+  if (rg.cur_left == 0) {
+    if (rg.runs_left <= 0) return;
+    rg.cur_off = rg.nxt.x; rg.cur_left = (int)rg.nxt.y;
+    --rg.runs_left;
+    if (++rg.ri == rg.len) rg.ri = 0;
+    rg.nxt = __ldg(rg.list + rg.ri);
+  }
+  const int nb = q3ring::imin(rg.SB, rg.cur_left);
   if (lane == 0) {
-    const uint32_t bytes = (d & 7u) << 10;
+    const uint32_t bytes = (uint32_t)nb << 10;
     const uint32_t bar = rg.full + 8u * rg.p_slot;
     mbar_expect_tx(bar, bytes);
-    const char* src = P.wbase + ((size_t)(d & ~63u) << 4);
+    const char* src = P.wbase + ((size_t)rg.cur_off << 4);
     if (P.flags & 4) bulk_g2s_plain(rg.slots + (uint32_t)(rg.p_slot * rg.SB) * 1024u, src, bytes, bar);
     else bulk_g2s(rg.slots + (uint32_t)(rg.p_slot * rg.SB) * 1024u, src, bytes, bar, policy);
   }
+  rg.cur_off += (uint32_t)nb << 6;
+  rg.cur_left -= nb;
   if (++rg.p_slot == rg.R) rg.p_slot = 0;
-  if (++rg.li == rg.len) rg.li = 0;
-  --rg.left;
   ++rg.outstanding;
-  rg.d0 = rg.d1;
-  rg.d1 = ring_desc(rg, 1);  // arrives long before it is needed (two refills ahead)
 }
 
 __device__ __forceinline__ void ring_release(Ring& rg, const KParams& P, int lane, uint64_t policy) {

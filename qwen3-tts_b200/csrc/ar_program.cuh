@@ -131,8 +131,8 @@ struct KParams {
   float keep_fraction;      // share of the code predictor's weight lines fetched with L2 evict_last priority
   int cp_phases;            // phases [0, cp_phases) of the frame program belong to the code predictor
   const char* wbase;        // lowest address of the packed GEMV weights (piece offsets are relative to it)
-  const uint32_t* pieces;   // piece table of this program: per (CTA, warp) the (offset/16 | blocks) of every ring piece of ONE pass
-  const uint32_t* piece_off;  // [grid*NWARPS + 1] start of each (CTA, warp) list in `pieces`
+  const uint2* runs;        // run table of this program: per (CTA, warp) the (offset/16, blocks) of every weight run of ONE pass
+  const uint32_t* run_off;  // [grid*NWARPS + 1] start of each (CTA, warp) list in `runs`
   unsigned long long* prof;  // [n_phases][grid][16]: globaltimer ns [0] phase end, [1] barrier passed, [2..4] inner marks, [6] start, [7],[8] warp-0 marks; cycles [5],[9],[10]
 };
 
