@@ -102,6 +102,22 @@ int q3_prefill(q3_engine* e, int32_t B, const void* embeds_dev, const int32_t* l
  * across calls (streaming = repeated calls with small max_frames).  Asynchronous. */
 int q3_decode(q3_engine* e, int32_t max_frames, int32_t* codes_dev, int32_t codes_stride, void* stream);
 
+/* ---- continuous batching (the reference has only the static padded batch of
+ * modeling_qwen3_tts.py:2239-2254 behind a Gradio queue, cli/demo.py:629).  A session owns n_slots rows; a finished or
+ * never-used slot is a row that keeps stepping and is ignored (exactly what HF does with finished rows of a batch).
+ * q3_admit prefills n new requests into free slots WHILE the others keep their state: their K/V, positions, sampling
+ * history and Philox streams are per row, so a request admitted at any frame generates what it would generate alone
+ * (keys_host[r] is the request's Philox row key).  q3_decode / q3_get_progress are shared with the static path;
+ * n_valid[b] counts the row's OWN frames, and the row's codes land at codes[b][0..n_valid).  q3_admit synchronises
+ * `stream` (it needs the frame counter).  embeds_dev: the n prompts packed back to back; trailing_dev: [n][stride][H]. */
+int q3_session_begin(q3_engine* e, int32_t n_slots, int32_t max_trailing, const void* tts_pad_dev, const q3_sampling* sp,
+                     void* stream);
+int q3_admit(q3_engine* e, int32_t n, const int32_t* slots_host, const uint32_t* keys_host, const void* embeds_dev,
+             const int32_t* lens_host, const void* trailing_dev, const int32_t* trailing_lens_host,
+             int32_t trailing_stride, void* stream);
+/* give up rows that reached their frame horizon without EOS (their slots become free) */
+int q3_release_slots(q3_engine* e, int32_t n, const int32_t* slots_host, void* stream);
+
 /* After synchronising `stream`: frames_done = frames whose 16 codes are complete (same for all rows);
  * n_valid[b] = frames of row b before its first EOS (== modeling_qwen3_tts.py:2283-2290 trim);
  * finished[b] = 1 once row b sampled EOS.  Host pointers (may be NULL). */

@@ -60,7 +60,8 @@ class SpkCfg(C.Structure):
 # every symbol include/qwen3tts_b200.h declares (tests/test_abi.py checks the header against this list)
 AR_SYMBOLS = ["q3_abi_version", "q3_last_error", "q3_engine_create", "q3_engine_destroy", "q3_engine_load_tensor",
               "q3_engine_finalize", "q3_prefill", "q3_decode", "q3_get_progress", "q3_set_debug",
-              "q3_algorithmic_bytes", "q3_set_profile", "q3_describe_frame_program", "q3_debug_time_phases", "q3_debug_set_skip"]
+              "q3_algorithmic_bytes", "q3_set_profile", "q3_describe_frame_program", "q3_debug_time_phases", "q3_debug_set_skip",
+              "q3_session_begin", "q3_admit", "q3_release_slots"]
 CODEC_SYMBOLS = ["q3_codec_create", "q3_codec_destroy", "q3_codec_load_tensor", "q3_codec_finalize",
                  "q3_codec_forward", "q3_codec_total_upsample", "q3_codec_last_launch_count",
                  "q3_codec_enc_create", "q3_codec_enc_destroy", "q3_codec_enc_load_tensor", "q3_codec_enc_finalize",
@@ -105,6 +106,9 @@ def load():
     lib.q3_engine_finalize.argtypes = [vp]
     lib.q3_prefill.argtypes = [vp, i32, vp, C.POINTER(i32), vp, C.POINTER(i32), i32, vp, C.POINTER(Sampling), vp]
     lib.q3_decode.argtypes = [vp, i32, vp, i32, vp]
+    lib.q3_session_begin.argtypes = [vp, i32, i32, vp, C.POINTER(Sampling), vp]
+    lib.q3_release_slots.argtypes = [vp, i32, C.POINTER(i32), vp]
+    lib.q3_admit.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(C.c_uint32), vp, C.POINTER(i32), vp, C.POINTER(i32), i32, vp]
     lib.q3_get_progress.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.q3_set_debug.argtypes = [vp, vp, i32, vp, vp]
     lib.q3_set_profile.argtypes = [vp, vp]

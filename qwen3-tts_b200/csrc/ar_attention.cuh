@@ -72,7 +72,7 @@ __device__ __noinline__ void attn_window_issue(const Phase& ph, const KParams& P
   const int si = min(unit / (nsplit * S.nkv), P.B - 1);
   u.seq = si; u.q0 = si;
   if (ph.seqmode == SEQ_CP) { u.nq = ph.nq; u.qstride = P.B; u.ctx_end = ph.ctx_end; }
-  else { u.nq = 1; u.qstride = 0; u.ctx_end = P.len0[si] + frame + 1; }
+  else { u.nq = 1; u.qstride = 0; u.ctx_end = max(1, min(P.len0[si] + frame + 1, S.cap)); }  // (clamp: finished rows of a session keep stepping)
   const int SL = (u.ctx_end + nsplit - 1) / nsplit;
   u.s0 = u.sp * SL;
   u.s1 = min(u.ctx_end, u.s0 + SL);

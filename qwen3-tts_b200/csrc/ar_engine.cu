@@ -215,7 +215,12 @@ struct q3_engine {
   int trailing_cap = 0;
   size_t trailing_alloc = 0;
   int max_len0 = 0, frames_issued = 0;
-  int len0[MAXB] = {0}, trailing_len[MAXB] = {0};
+  int len0[MAXB] = {0}, trailing_len[MAXB] = {0};   // len0 is stored as prompt length - frame0 (see KParams)
+  int frame0[MAXB] = {0};
+  unsigned int row_key[MAXB] = {0};
+  bool active[MAXB] = {false};
+  bool session = false;       // continuous-batching session (q3_session_begin / q3_admit)
+  unsigned int admit_mask = 0xffffffffu;
   unsigned char* seen = nullptr;
   float* split_buf = nullptr;
   Phase* prog_dev = nullptr;
@@ -718,6 +723,8 @@ static int launch_program(q3_engine* e, int off, int n, int mode, int max_iters,
   P.B = e->B;
   for (int b = 0; b < MAXB; ++b) { P.len0[b] = e->len0[b]; P.trailing_len[b] = e->trailing_len[b]; }
   P.max_len0 = e->max_len0;
+  for (int b = 0; b < MAXB; ++b) { P.frame0[b] = e->frame0[b]; P.row_key[b] = e->row_key[b]; }
+  P.admit_mask = e->admit_mask;
   P.emb_t = e->plain["talker.codec_embedding"]; P.emb_cp = e->plain["cp.codec_embedding"];
   P.x_cp = e->cfg.has_cp_projection ? e->x_cp : e->cp.h; P.past_hidden = e->past_hidden; P.trailing = e->trailing; P.trailing_stride = e->trailing_cap;
   if (e->proj_tab) { P.cp_next = e->proj_tab; P.cp_next_dst = e->cp.h; P.cp_next_w = e->cfg.cp.hidden_size; }
@@ -736,51 +743,16 @@ static int launch_program(q3_engine* e, int off, int n, int mode, int max_iters,
   return 0;
 }
 
-extern "C" int q3_prefill(q3_engine* e, int32_t B, const void* embeds_dev, const int32_t* lens_host,
-                          const void* trailing_dev, const int32_t* trailing_lens_host, int32_t trailing_stride,
-                          const void* tts_pad_dev, const q3_sampling* sp, void* stream_) {
-  Q3_REQUIRE(e && e->finalized, "engine not finalized");
-  Q3_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch %d out of range", B);
-  Q3_REQUIRE(embeds_dev && lens_host && tts_pad_dev && sp, "null argument");
-  Q3_CUDA(cudaSetDevice(e->cfg.device));
-  cudaStream_t stream = (cudaStream_t)stream_;
-  if (build_programs(e, B)) return 1;
-  e->B = B; e->sp = *sp;
+// Prefill of `n` prompts (packed back to back in embeds_dev) into the engine slots slots[0..n): tcgen05 GEMMs over all
+// their tokens at once, K/V into the slots' cache rows, then the head GEMV + the first codebook-0 sample of exactly
+// those rows (admit_mask).  Shared by the static batch (q3_prefill) and by continuous batching (q3_admit).
+static int prefill_rows(q3_engine* e, int n, const int* slots, const void* embeds_dev, const int32_t* lens_host, cudaStream_t stream) {
   const int H = e->cfg.talker.hidden_size;
-  // per-request state reset
-  DevState hs;
-  memset(&hs, 0, sizeof(hs));
-  hs.B = B;
-  for (int b = 0; b < B; ++b) {
-    Q3_REQUIRE(lens_host[b] >= 1 && lens_host[b] < e->cfg.max_ctx, "prompt length %d out of range", lens_host[b]);
-    hs.len0[b] = lens_host[b];
-    e->len0[b] = lens_host[b];
-    e->max_len0 = b == 0 ? lens_host[b] : std::max(e->max_len0, lens_host[b]);
-    hs.trailing_len[b] = trailing_lens_host ? trailing_lens_host[b] : 0;
-    e->trailing_len[b] = hs.trailing_len[b];
-    Q3_REQUIRE(hs.trailing_len[b] <= trailing_stride, "trailing length exceeds stride");
-  }
-  Q3_CUDA(cudaMemcpyAsync(e->st, &hs, sizeof(hs), cudaMemcpyHostToDevice, stream));
-  Q3_CUDA(cudaMemsetAsync(e->seen, 0, (size_t)MAXB * e->cfg.talker.vocab_size, stream));
-  Q3_CUDA(cudaMemcpyAsync(e->tts_pad, tts_pad_dev, (size_t)H * 2, cudaMemcpyDeviceToDevice, stream));
-  if (trailing_stride > 0 && trailing_dev) {
-    const size_t need = (size_t)MAXB * trailing_stride * H;
-    if (need > e->trailing_alloc) {  // (re)allocate the engine-owned copy of trailing_text_hidden
-      Q3_CUDA(cudaStreamSynchronize(stream));  // growth only: earlier launches may still read the old buffer
-      e->release(e->trailing);
-      if (e->alloc(&e->trailing, need)) return 1;
-      e->trailing_alloc = need;
-    }
-    Q3_CUDA(cudaMemcpyAsync(e->trailing, trailing_dev, (size_t)B * trailing_stride * H * 2, cudaMemcpyDeviceToDevice, stream));
-  }
-  e->trailing_cap = trailing_stride;
-  e->codes_stride = 0;
-  e->frames_issued = 0;
-  // ---- prefill on tensor cores: all prompt tokens of all rows at once (packed [ntok][H], rows back to back)
   PfLens pl{};
-  pl.B = B;
-  for (int b = 0; b < B; ++b) pl.start[b + 1] = pl.start[b] + lens_host[b];
-  const int ntok = pl.start[B];
+  pl.B = n;
+  unsigned int mask = 0;
+  for (int r = 0; r < n; ++r) { pl.start[r + 1] = pl.start[r] + lens_host[r]; pl.slot[r] = slots[r]; mask |= 1u << slots[r]; }
+  const int ntok = pl.start[n];
   const q3_stack_cfg& tc = e->cfg.talker;
   const int nh = tc.num_heads, nkv = tc.num_kv_heads, I = tc.intermediate_size, QKV = (nh + 2 * nkv) * HD;
   if (ntok > e->pf_cap) {
@@ -824,10 +796,135 @@ extern "C" int q3_prefill(q3_engine* e, int32_t B, const void* embeds_dev, const
     { GemmEpilogue ep{}; ep.resid = e->pf_x; ep.out_raw = e->pf_x; if (gemm(e->pf_act, I, p + ".down", H, ep)) return 1; }
   }
   Q3_CUDA(cudaGetLastError());
-  pf_gather_last_kernel<<<B, 128, 0, stream>>>(pl, e->pf_x, e->h_last, H);
-  // head + sample codebook-0 of frame 0 (codes are materialised by q3_decode's first call via st->c0)
-  if (launch_program(e, e->off_head, (int)e->prog_head.size(), 0, 1, e->nt_head, e->plan_head, e->pt_head, nullptr, stream)) return 1;
+  pf_gather_last_kernel<<<n, 128, 0, stream>>>(pl, e->pf_x, e->h_last, H);
+  // head + sample codebook-0 of the rows' first frame (codes are materialised by the following q3_decode via st->c0)
+  e->admit_mask = mask;
+  const int rc = launch_program(e, e->off_head, (int)e->prog_head.size(), 0, 1, e->nt_head, e->plan_head, e->pt_head, nullptr, stream);
+  e->admit_mask = 0xffffffffu;
+  return rc;
+}
+
+static int ensure_trailing(q3_engine* e, int stride, cudaStream_t stream) {
+  const size_t need = (size_t)MAXB * stride * e->cfg.talker.hidden_size;
+  if (need > e->trailing_alloc) {  // (re)allocate the engine-owned copy of trailing_text_hidden
+    Q3_CUDA(cudaStreamSynchronize(stream));  // growth only: earlier launches may still read the old buffer
+    e->release(e->trailing);
+    e->trailing = nullptr;
+    if (e->alloc(&e->trailing, need)) return 1;
+    e->trailing_alloc = need;
+  }
   return 0;
+}
+
+extern "C" int q3_prefill(q3_engine* e, int32_t B, const void* embeds_dev, const int32_t* lens_host,
+                          const void* trailing_dev, const int32_t* trailing_lens_host, int32_t trailing_stride,
+                          const void* tts_pad_dev, const q3_sampling* sp, void* stream_) {
+  Q3_REQUIRE(e && e->finalized, "engine not finalized");
+  Q3_REQUIRE(B >= 1 && B <= e->cfg.max_batch, "batch %d out of range", B);
+  Q3_REQUIRE(embeds_dev && lens_host && tts_pad_dev && sp, "null argument");
+  Q3_CUDA(cudaSetDevice(e->cfg.device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (build_programs(e, B)) return 1;
+  e->B = B; e->sp = *sp; e->session = false;
+  const int H = e->cfg.talker.hidden_size;
+  // per-request state reset
+  DevState hs;
+  memset(&hs, 0, sizeof(hs));
+  hs.B = B;
+  int slots[MAXB];
+  for (int b = 0; b < MAXB; ++b) { e->frame0[b] = 0; e->row_key[b] = (unsigned int)b; e->active[b] = b < B; }
+  for (int b = 0; b < B; ++b) {
+    Q3_REQUIRE(lens_host[b] >= 1 && lens_host[b] < e->cfg.max_ctx, "prompt length %d out of range", lens_host[b]);
+    hs.len0[b] = lens_host[b];
+    e->len0[b] = lens_host[b];
+    e->max_len0 = b == 0 ? lens_host[b] : std::max(e->max_len0, lens_host[b]);
+    hs.trailing_len[b] = trailing_lens_host ? trailing_lens_host[b] : 0;
+    e->trailing_len[b] = hs.trailing_len[b];
+    Q3_REQUIRE(hs.trailing_len[b] <= trailing_stride, "trailing length exceeds stride");
+    slots[b] = b;
+  }
+  Q3_CUDA(cudaMemcpyAsync(e->st, &hs, sizeof(hs), cudaMemcpyHostToDevice, stream));
+  Q3_CUDA(cudaMemsetAsync(e->seen, 0, (size_t)MAXB * e->cfg.talker.vocab_size, stream));
+  Q3_CUDA(cudaMemcpyAsync(e->tts_pad, tts_pad_dev, (size_t)H * 2, cudaMemcpyDeviceToDevice, stream));
+  if (trailing_stride > 0 && trailing_dev) {
+    if (ensure_trailing(e, trailing_stride, stream)) return 1;
+    Q3_CUDA(cudaMemcpyAsync(e->trailing, trailing_dev, (size_t)B * trailing_stride * H * 2, cudaMemcpyDeviceToDevice, stream));
+  }
+  e->trailing_cap = trailing_stride;
+  e->codes_stride = 0;
+  e->frames_issued = 0;
+  return prefill_rows(e, B, slots, embeds_dev, lens_host, stream);
+}
+
+// ---- continuous batching: a session of n_slots rows that start and finish independently ------------
+extern "C" int q3_session_begin(q3_engine* e, int32_t n_slots, int32_t max_trailing, const void* tts_pad_dev, const q3_sampling* sp,
+                                void* stream_) {
+  Q3_REQUIRE(e && e->finalized, "engine not finalized");
+  Q3_REQUIRE(n_slots >= 1 && n_slots <= e->cfg.max_batch, "n_slots %d out of range", n_slots);
+  Q3_REQUIRE(tts_pad_dev && sp && max_trailing >= 0, "bad argument");
+  Q3_CUDA(cudaSetDevice(e->cfg.device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (build_programs(e, n_slots)) return 1;
+  e->B = n_slots; e->sp = *sp; e->session = true;
+  DevState hs;
+  memset(&hs, 0, sizeof(hs));
+  hs.B = n_slots;
+  for (int b = 0; b < MAXB; ++b) {
+    hs.finished[b] = 1;  // an empty slot is a finished row: it keeps stepping (like HF's padded rows) and is ignored
+    hs.len0[b] = 1;
+    e->len0[b] = 1; e->frame0[b] = 0; e->row_key[b] = (unsigned int)b; e->trailing_len[b] = 0; e->active[b] = false;
+  }
+  e->max_len0 = 1;
+  Q3_CUDA(cudaMemcpyAsync(e->st, &hs, sizeof(hs), cudaMemcpyHostToDevice, stream));
+  Q3_CUDA(cudaMemsetAsync(e->seen, 0, (size_t)MAXB * e->cfg.talker.vocab_size, stream));
+  Q3_CUDA(cudaMemcpyAsync(e->tts_pad, tts_pad_dev, (size_t)e->cfg.talker.hidden_size * 2, cudaMemcpyDeviceToDevice, stream));
+  if (max_trailing > 0 && ensure_trailing(e, max_trailing, stream)) return 1;
+  e->trailing_cap = max_trailing;
+  e->codes_stride = 0;
+  e->frames_issued = 0;
+  return 0;
+}
+
+extern "C" int q3_admit(q3_engine* e, int32_t n, const int32_t* slots_host, const uint32_t* keys_host, const void* embeds_dev,
+                        const int32_t* lens_host, const void* trailing_dev, const int32_t* trailing_lens_host,
+                        int32_t trailing_stride, void* stream_) {
+  Q3_REQUIRE(e && e->finalized && e->session, "q3_session_begin first");
+  Q3_REQUIRE(n >= 1 && n <= e->B && slots_host && keys_host && embeds_dev && lens_host, "bad argument");
+  Q3_CUDA(cudaSetDevice(e->cfg.device));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  // the global frame at which these rows start = frames completed so far (a decode may have stopped early)
+  DevState hs;
+  Q3_CUDA(cudaStreamSynchronize(stream));
+  Q3_CUDA(cudaMemcpy(&hs, e->st, sizeof(hs), cudaMemcpyDeviceToHost));
+  Q3_REQUIRE(hs.error == 0, "device-side error %d", hs.error);
+  const int F = hs.step;
+  e->frames_issued = F;
+  const int H = e->cfg.talker.hidden_size;
+  AdmitRows A{};
+  A.n = n;
+  int slots[MAXB];
+  for (int r = 0; r < n; ++r) {
+    const int b = slots_host[r];
+    Q3_REQUIRE(b >= 0 && b < e->B, "slot %d out of range", b);
+    Q3_REQUIRE(hs.finished[b] != 0 || !e->active[b], "slot %d is still running (q3_release_slots it first)", b);
+    for (int q = 0; q < r; ++q) Q3_REQUIRE(slots_host[q] != b, "slot %d admitted twice", b);
+    Q3_REQUIRE(lens_host[r] >= 1 && lens_host[r] < e->cfg.max_ctx, "prompt length %d out of range", lens_host[r]);
+    const int tl = trailing_lens_host ? trailing_lens_host[r] : 0;
+    Q3_REQUIRE(tl <= trailing_stride && tl <= e->trailing_cap, "trailing length %d exceeds the session's max_trailing %d", tl, e->trailing_cap);
+    slots[r] = b;
+    A.slot[r] = b; A.len0[r] = lens_host[r]; A.trailing_len[r] = tl;
+    e->len0[b] = lens_host[r] - F; e->frame0[b] = F; e->row_key[b] = keys_host[r]; e->trailing_len[b] = tl; e->active[b] = true;
+    if (tl > 0)
+      Q3_CUDA(cudaMemcpyAsync(e->trailing + (size_t)b * e->trailing_cap * H, reinterpret_cast<const bf16*>(trailing_dev) + (size_t)r * trailing_stride * H,
+                              (size_t)tl * H * 2, cudaMemcpyDeviceToDevice, stream));
+  }
+  for (int b = 0; b < e->B; ++b)
+    if (hs.finished[b] && !std::count(slots, slots + n, b)) e->active[b] = false;
+  e->max_len0 = 1;
+  for (int b = 0; b < e->B; ++b)
+    if (e->active[b]) e->max_len0 = std::max(e->max_len0, e->len0[b]);
+  admit_state_kernel<<<n, 256, 0, stream>>>(e->st, A, e->seen, e->cfg.talker.vocab_size);
+  return prefill_rows(e, n, slots, embeds_dev, lens_host, stream);
 }
 
 extern "C" int q3_decode(q3_engine* e, int32_t max_frames, int32_t* codes_dev, int32_t codes_stride, void* stream_) {
@@ -836,10 +933,26 @@ extern "C" int q3_decode(q3_engine* e, int32_t max_frames, int32_t* codes_dev, i
   Q3_CUDA(cudaSetDevice(e->cfg.device));
   cudaStream_t stream = (cudaStream_t)stream_;
   e->codes_stride = codes_stride;
-  Q3_REQUIRE(e->max_len0 + e->frames_issued + max_frames <= e->cfg.max_ctx, "KV capacity exceeded: prompt %d + %d frames > max_ctx %d",
-             e->max_len0, e->frames_issued + max_frames, e->cfg.max_ctx);
+  for (int b = 0; b < e->B; ++b)  // len0 holds prompt length - frame0: position of the last frame = len0 + frames issued
+    if (e->active[b])
+      Q3_REQUIRE(e->len0[b] + e->frames_issued + max_frames <= e->cfg.max_ctx,
+                 "KV capacity exceeded: row %d would reach position %d > max_ctx %d", b, e->len0[b] + e->frames_issued + max_frames, e->cfg.max_ctx);
   e->frames_issued += max_frames;
   return launch_program(e, e->off_frame, (int)e->prog_frame.size(), 1, max_frames, e->nt_frame, e->plan_frame, e->pt_frame, codes_dev, stream);
+}
+
+extern "C" int q3_release_slots(q3_engine* e, int32_t n, const int32_t* slots_host, void* stream_) {
+  Q3_REQUIRE(e && e->session && slots_host && n >= 0 && n <= MAXB, "bad argument");
+  Q3_CUDA(cudaSetDevice(e->cfg.device));
+  AdmitRows A{};
+  A.n = n;
+  for (int r = 0; r < n; ++r) {
+    Q3_REQUIRE(slots_host[r] >= 0 && slots_host[r] < e->B, "slot %d out of range", slots_host[r]);
+    A.slot[r] = slots_host[r];
+    e->active[slots_host[r]] = false;
+  }
+  if (n > 0) release_state_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(e->st, A);
+  return 0;
 }
 
 extern "C" int q3_get_progress(q3_engine* e, int32_t* frames_done, int32_t* n_valid, int32_t* finished) {
@@ -850,7 +963,8 @@ extern "C" int q3_get_progress(q3_engine* e, int32_t* frames_done, int32_t* n_va
   Q3_REQUIRE(hs.error == 0, "device-side error %d (grid barrier timeout)", hs.error);
   if (frames_done) *frames_done = hs.step;
   for (int b = 0; b < e->B; ++b) {
-    if (n_valid) n_valid[b] = hs.finished[b] ? hs.n_valid[b] : hs.step;
+    if (n_valid) n_valid[b] = hs.finished[b] ? hs.n_valid[b] : hs.step - e->frame0[b];  // the row's own frame count
+    if (hs.finished[b]) e->active[b] = false;
     if (finished) finished[b] = hs.finished[b];
   }
   return 0;

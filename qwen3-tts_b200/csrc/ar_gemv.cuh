@@ -250,8 +250,8 @@ __device__ __forceinline__ uint32_t norm_pair(uint32_t x2, uint32_t w2, float in
 // independent 16-byte loads first, the RMSNorm runs on the registers (sum of squares -> warp reduce -> scale) and the
 // result is written to smem once.  The norm weights sit in nw_s (fetched before the preceding grid barrier).
 // (Un-normed inputs are copied by the TMA unit, see gemv_phase.)  K <= 2048.
-__device__ __forceinline__ void stage_columns(const bf16* __restrict__ src, int src_ld, float eps, bf16* __restrict__ save, int K,
-                                              int nc, char* __restrict__ xs, int xstride, const uint4* __restrict__ nw_s) {
+__device__ __forceinline__ void stage_columns(const bf16* __restrict__ src, int src_ld, float eps, bf16* __restrict__ save, unsigned int save_mask,
+                                              int K, int nc, char* __restrict__ xs, int xstride, const uint4* __restrict__ nw_s) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = K >> 3;
 #pragma unroll 1
@@ -284,7 +284,7 @@ __device__ __forceinline__ void stage_columns(const bf16* __restrict__ src, int 
         o.y = norm_pair(v[i].y, w.y, inv);
         o.z = norm_pair(v[i].z, w.z, inv);
         o.w = norm_pair(v[i].w, w.w, inv);
-        if (save) reinterpret_cast<uint4*>(save + (size_t)col * K)[lane + 32 * i] = o;
+        if (save && ((save_mask >> col) & 1u)) reinterpret_cast<uint4*>(save + (size_t)col * K)[lane + 32 * i] = o;
         drow[lane + 32 * i] = o;
       }
     }
@@ -384,7 +384,7 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
   // ---- activations -> shared memory
   if (staged && (ntc > 0 || save) && !(P.flags & 32)) {
     if (normed) {
-      stage_columns(src, src_ld, ph.eps, save, K, nc, xs, xstride, nw_s);
+      stage_columns(src, src_ld, ph.eps, save, P.mode == 0 ? P.admit_mask : 0xffffffffu, K, nc, xs, xstride, nw_s);
     } else {
       // plain copy of nc contiguous rows: one bulk (TMA) copy per column, completion on the CTA's x barrier
       if (tid == 0) {

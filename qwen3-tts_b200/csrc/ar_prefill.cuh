@@ -41,20 +41,39 @@ __global__ void pf_rmsnorm_kernel(const bf16* __restrict__ x, const bf16* __rest
 
 // packed-token index (row, position) of all prompt tokens, built on the device from the prompt lengths (passed by
 // value: no host staging buffer, no synchronisation), and the gather of every row's last hidden state
-struct PfLens { int B; int start[MAXB + 1]; };
+struct PfLens { int B; int start[MAXB + 1]; int slot[MAXB]; };  // row r of the packed prompt batch lives in engine slot slot[r]
 __global__ void pf_index_kernel(PfLens L, int* __restrict__ tok_seq, int* __restrict__ tok_pos) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= L.start[L.B]) return;
   int b = 0;
   while (i >= L.start[b + 1]) ++b;
-  tok_seq[i] = b;
+  tok_seq[i] = L.slot[b];
   tok_pos[i] = i - L.start[b];
 }
 __global__ void pf_gather_last_kernel(PfLens L, const bf16* __restrict__ x, bf16* __restrict__ h_last, int H) {
   const int b = blockIdx.x;
   const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)(L.start[b + 1] - 1) * H);
-  uint4* dst = reinterpret_cast<uint4*>(h_last + (size_t)b * H);
+  uint4* dst = reinterpret_cast<uint4*>(h_last + (size_t)L.slot[b] * H);
   for (int i = threadIdx.x; i < H / 8; i += blockDim.x) dst[i] = src[i];
+}
+
+// continuous batching: (re)initialise the device-side state of the slots that receive a new request
+struct AdmitRows { int n; int slot[MAXB]; int len0[MAXB]; int trailing_len[MAXB]; };
+__global__ void admit_state_kernel(DevState* st, AdmitRows A, unsigned char* seen, int V) {
+  const int r = blockIdx.x, b = A.slot[r];
+  if (threadIdx.x == 0) {
+    st->finished[b] = 0; st->n_valid[b] = 0; st->n_gen[b] = 0; st->c0[b] = 0;
+    st->len0[b] = A.len0[r]; st->trailing_len[b] = A.trailing_len[r];
+  }
+  for (int i = threadIdx.x; i < V; i += blockDim.x) seen[(size_t)b * V + i] = 0;
+}
+
+// a row that is abandoned at its frame horizon: mark it finished (it keeps stepping like any finished row)
+__global__ void release_state_kernel(DevState* st, AdmitRows A) {
+  if ((int)threadIdx.x < A.n && !st->finished[A.slot[threadIdx.x]]) {
+    st->finished[A.slot[threadIdx.x]] = 1;
+    st->n_valid[A.slot[threadIdx.x]] = 0x3fffffff;  // "never sampled EOS": the host caps it at the frames it asked for
+  }
 }
 
 // per (token, head-vector): q heads RMSNorm+RoPE in place; k head -> K cache (normed, roped); v head -> V cache

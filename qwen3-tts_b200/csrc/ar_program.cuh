@@ -103,7 +103,11 @@ struct KParams {
   int G, eos, has_proj;
   int B;                    // sequences in this request (constant per launch)
   int len0[MAXB];           // prompt lengths
-  int max_len0;             // longest prompt of the batch (attention split count)
+  int max_len0;             // longest (prompt - frame0) of the batch (attention split count)
+  int frame0[MAXB];         // global frame index at which row b was admitted (continuous batching; 0 for a static batch):
+                            // the row's own frame counter is frame - frame0[b]; len0[b] is stored as prompt_len - frame0[b]
+  unsigned int row_key[MAXB];  // Philox row key (the request's identity, not its slot: an admitted row samples what it would alone)
+  unsigned int admit_mask;  // prefill-head program only: rows whose first token is sampled / whose hidden state is saved
   int trailing_len[MAXB];
   q3_sampling sp;
   // sampler / embed resources

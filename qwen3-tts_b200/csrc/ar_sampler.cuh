@@ -64,6 +64,8 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, const KParams& P, 
   DevState* st = P.st;
   const int B = P.B;
   if (b >= B) return;
+  if (in_prefill && !((P.admit_mask >> b) & 1u)) return;  // admission prefill: rows already running keep their state
+  frame -= P.frame0[b];  // the row's own frame counter (continuous batching admits rows at different global frames)
   const int tid = threadIdx.x;
   const int group = ph.group;
   const bool talker = group == 0;
@@ -191,7 +193,7 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, const KParams& P, 
 #pragma unroll 1
     for (int w = 0; w < NWARPS; ++w) { if (w < wp) base += red[w]; total += red[w]; }
     const float excl = base + incl - loc;
-    const float u = philox_uniform(P.sp.seed, (uint32_t)b, (uint32_t)fidx, (uint32_t)group);
+    const float u = philox_uniform(P.sp.seed, P.row_key[b], (uint32_t)fidx, (uint32_t)group);
     const float target = u * total;
     int cand = 0x7fffffff, lastpos = -1;
     float run = excl;
@@ -237,7 +239,7 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, const KParams& P, 
     const int j = group;  // codebook index 1..G-1
     if (tid == 0) {
       st->cur[b][j] = tok;
-      if (P.codes_out && frame < P.codes_stride) {
+      if (P.codes_out && frame >= 0 && frame < P.codes_stride) {
         int* row = P.codes_out + ((size_t)b * P.codes_stride + frame) * P.G;
         row[j] = tok;
         if (j == 1) row[0] = ldcgi(&st->cur[b][0]);

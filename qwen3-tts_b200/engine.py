@@ -147,6 +147,45 @@ class AREngine:
         _lib.check(self.lib.q3_prefill(self.h, B, emb.data_ptr(), lens, trp, tlen, Tt, pad.data_ptr(), C.byref(s),
                                        C.c_void_p(stream)))
 
+    # ------------------------------------------------------------------ continuous batching (low level)
+    def session_begin(self, n_slots: int, tts_pad_embed: torch.Tensor, sp: SamplingParams, max_trailing: int = 0):
+        """Start a session of `n_slots` independent rows (all empty).  See include/qwen3tts_b200.h: q3_session_begin."""
+        H = self.cfg.talker.hidden_size
+        pad = tts_pad_embed.reshape(H).to(self.device, torch.bfloat16).contiguous()
+        s = self._sampling(sp)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._B = n_slots
+        self._hold = (pad,)
+        _lib.check(self.lib.q3_session_begin(self.h, int(n_slots), int(max_trailing), pad.data_ptr(), C.byref(s), C.c_void_p(stream)))
+
+    def admit(self, slots: Sequence[int], keys: Sequence[int], inputs_embeds: Sequence[torch.Tensor],
+              trailing_text: Sequence[torch.Tensor]):
+        """Prefill new requests into free slots of the running session (q3_admit)."""
+        n = len(slots)
+        H = self.cfg.talker.hidden_size
+        dev = self.device
+        emb = torch.cat([e.reshape(-1, H) for e in inputs_embeds], 0).to(dev, torch.bfloat16).contiguous()
+        lens = (C.c_int32 * n)(*[int(e.reshape(-1, H).shape[0]) for e in inputs_embeds])
+        tl = [int(t.reshape(-1, H).shape[0]) for t in trailing_text]
+        Tt = max(tl) if tl else 0
+        if Tt > 0:
+            tr = torch.zeros(n, Tt, H, dtype=torch.bfloat16, device=dev)
+            for i, t in enumerate(trailing_text):
+                if tl[i]:
+                    tr[i, :tl[i]] = t.reshape(-1, H).to(dev, torch.bfloat16)
+            trp = tr.data_ptr()
+        else:
+            tr, trp = None, None
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self._hold = self._hold + (emb, tr)
+        _lib.check(self.lib.q3_admit(self.h, n, (C.c_int32 * n)(*[int(x) for x in slots]), (C.c_uint32 * n)(*[int(k) & 0xffffffff for k in keys]),
+                                     emb.data_ptr(), lens, trp, (C.c_int32 * n)(*tl), Tt, C.c_void_p(stream)))
+
+    def release_slots(self, slots: Sequence[int]):
+        n = len(slots)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.lib.q3_release_slots(self.h, n, (C.c_int32 * max(n, 1))(*[int(x) for x in slots]), C.c_void_p(stream)))
+
     def decode(self, max_frames: int, codes: torch.Tensor):
         """codes: int32 [B][stride][G] device tensor that accumulates frames across calls."""
         assert codes.dtype == torch.int32 and codes.is_cuda and codes.is_contiguous()
