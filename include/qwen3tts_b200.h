@@ -169,6 +169,21 @@ int q3_codec_finalize(q3_codec* c);
 /* One full causal forward == Qwen3TTSTokenizerV2Decoder.forward (…v2.py:869-884).
  * codes: int32 [B][K][T] device; wav: fp32 [B][T*upsample] device.  Asynchronous. */
 int q3_codec_forward(q3_codec* c, const int32_t* codes_dev, int32_t B, int32_t T, float* wav_dev, void* stream);
+
+/* ---- stateful streaming decoder.  The reference decodes whole utterances, or chunks with 25
+ * re-decoded frames of left context (chunked_decode, tokenizer_12hz/modeling_qwen3_tts_tokenizer_v2.py:886-896); this
+ * handle carries the decoder's causal state instead (conv tails, ConvTranspose overlap row, 71 frames of rotated K/V
+ * per transformer layer), so pushing packets of any sizes yields exactly the waveform of the full causal forward
+ * (…v2.py:869-884) over everything pushed, with only the NEW frames' work per packet.
+ * open: B rows, packets of <= max_packet_frames frames.  step: codes_dev int32 [B][num_quantizers][n] (the next n
+ * frames of every row) -> wav_dev fp32 [B][n * total_upsample]; asynchronous on `stream`.  reset: start new
+ * utterances in all rows.  The position (frames pushed) must stay below the engine's max_frames (RoPE table). */
+typedef struct q3_codec_stream q3_codec_stream;
+int q3_codec_stream_open(q3_codec* c, int32_t B, int32_t max_packet_frames, q3_codec_stream** out);
+int q3_codec_stream_step(q3_codec_stream* s, const int32_t* codes_dev, int32_t n, float* wav_dev, void* stream);
+int q3_codec_stream_reset(q3_codec_stream* s, void* stream);
+int q3_codec_stream_position(q3_codec_stream* s);
+void q3_codec_stream_close(q3_codec_stream* s);
 int q3_codec_total_upsample(q3_codec* c);
 /* kernels launched by the last q3_codec_forward (bench.py's gpu_launches bookkeeping) */
 int q3_codec_last_launch_count(q3_codec* c);

@@ -64,6 +64,7 @@ AR_SYMBOLS = ["q3_abi_version", "q3_last_error", "q3_engine_create", "q3_engine_
               "q3_session_begin", "q3_admit", "q3_release_slots"]
 CODEC_SYMBOLS = ["q3_codec_create", "q3_codec_destroy", "q3_codec_load_tensor", "q3_codec_finalize",
                  "q3_codec_forward", "q3_codec_total_upsample", "q3_codec_last_launch_count",
+                 "q3_codec_stream_open", "q3_codec_stream_step", "q3_codec_stream_reset", "q3_codec_stream_position", "q3_codec_stream_close",
                  "q3_codec_enc_create", "q3_codec_enc_destroy", "q3_codec_enc_load_tensor", "q3_codec_enc_finalize",
                  "q3_codec_enc_encode", "q3_codec_enc_frames", "q3_codec_enc_hop", "q3_codec_enc_last_launch_count",
                  "q3_codec_enc_debug_capture",
@@ -123,6 +124,12 @@ def load():
         lib.q3_codec_load_tensor.argtypes = [vp, C.c_char_p, vp, C.POINTER(i64), i32]
         lib.q3_codec_finalize.argtypes = [vp]
         lib.q3_codec_forward.argtypes = [vp, vp, i32, i32, vp, vp]
+        lib.q3_codec_stream_open.argtypes = [vp, i32, i32, C.POINTER(vp)]
+        lib.q3_codec_stream_step.argtypes = [vp, vp, i32, vp, vp]
+        lib.q3_codec_stream_reset.argtypes = [vp, vp]
+        lib.q3_codec_stream_position.argtypes = [vp]
+        lib.q3_codec_stream_close.argtypes = [vp]
+        lib.q3_codec_stream_close.restype = None
         lib.q3_codec_total_upsample.argtypes = [vp]
         lib.q3_codec_last_launch_count.argtypes = [vp]
         lib.q3_codec_enc_create.argtypes = [C.POINTER(CodecEncCfg), C.POINTER(vp)]

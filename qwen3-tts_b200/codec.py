@@ -197,6 +197,11 @@ class CodecDecoder:
         self._keep = c
         return wav[:, None, :]
 
+    def open_stream(self, batch: int, max_packet_frames: int = 8) -> "CodecStream":
+        """Stateful streaming decoder over `batch` rows (q3_codec_stream_*): push packets, get exactly the waveform of
+        the full causal forward over everything pushed, for the cost of the new frames only."""
+        return CodecStream(self, batch, max_packet_frames)
+
     @torch.no_grad()
     def chunked_decode(self, codes, chunk_size=300, left_context_size=25):
         """…v2.py:886-896, replicated exactly (chunks with 25 frames of left context)."""
@@ -218,3 +223,50 @@ class CodecDecoder:
         codes = torch.clamp(audio_codes, min=0)
         wav = self.chunked_decode(codes.transpose(1, 2)).squeeze(1)
         return [a[:int(l)] for a, l in zip(wav, lengths)]
+
+
+class CodecStream:
+    """Handle on a q3_codec_stream (conv tails, ConvTranspose overlap rows and 71 frames of rotated K/V per transformer
+    layer live on the device).  `push(codes (B,K,n))` -> wav (B,1,n*upsample) of those n frames."""
+
+    def __init__(self, dec: CodecDecoder, batch: int, max_packet_frames: int = 8):
+        self.dec, self.B, self.nmax = dec, int(batch), int(max_packet_frames)
+        h = C.c_void_p()
+        _lib.check(dec.lib.q3_codec_stream_open(dec.h, self.B, self.nmax, C.byref(h)))
+        self.h = h
+
+    @property
+    def position(self) -> int:
+        return int(self.dec.lib.q3_codec_stream_position(self.h))
+
+    @torch.no_grad()
+    def push(self, codes: torch.Tensor) -> torch.Tensor:
+        dec = self.dec
+        if codes.dim() != 3 or codes.shape[0] != self.B or codes.shape[1] != dec.cfg.num_quantizers:
+            raise ValueError(f"expected codes of shape ({self.B}, {dec.cfg.num_quantizers}, n), got {tuple(codes.shape)}")
+        n = int(codes.shape[2])
+        out = []
+        for s0 in range(0, n, self.nmax):  # longer pushes are cut into packets of the stream's capacity
+            c = codes[:, :, s0:s0 + self.nmax].to(dec.device, torch.int32).contiguous()
+            m = int(c.shape[2])
+            wav = torch.empty(self.B, m * dec.total_upsample, dtype=torch.float32, device=dec.device)
+            stream = torch.cuda.current_stream(dec.device).cuda_stream
+            _lib.check(dec.lib.q3_codec_stream_step(self.h, c.data_ptr(), m, wav.data_ptr(), C.c_void_p(stream)))
+            self._keep = c
+            out.append(wav)
+        return torch.cat(out, 1)[:, None, :] if out else torch.zeros(self.B, 1, 0, device=dec.device)
+
+    def reset(self):
+        stream = torch.cuda.current_stream(self.dec.device).cuda_stream
+        _lib.check(self.dec.lib.q3_codec_stream_reset(self.h, C.c_void_p(stream)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.dec.lib.q3_codec_stream_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
         const int tap = kb / kpb, k0 = (kb - tap * kpb) * BK;
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
         mbar_expect_tx(full0 + 8 * s, A_BYTES + b_bytes);
-        tma_load_3d(sa, &p.tmA, k0, m0 + p.shift[tap], b, full0 + 8 * s);
+        tma_load_3d(sa, &p.tmA, k0, m0 + p.shift[tap] + p.a_row0, b, full0 + 8 * s);
         tma_load_2d(sb, &p.tmW, tap * p.Kp + k0, n0, full0 + 8 * s);
       }
     }
@@ -151,7 +151,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const GemmEpilogue& E = p.ep;
     const bool row_ok = m < p.T;
-    const size_t row_off = ((size_t)b * p.T + (row_ok ? m : 0)) * (size_t)p.N;
+    const size_t mrow = (size_t)(row_ok ? m : 0) * (size_t)p.N;
+    const size_t raw_off = (size_t)b * (size_t)p.raw_bs + mrow, act_off = (size_t)b * (size_t)p.act_bs + mrow,
+                 res_off = (size_t)b * (size_t)p.resid_bs + mrow;
     for (int c0 = 0; c0 < p.bn; c0 += 16) {
       uint32_t v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
@@ -173,8 +175,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
         for (int i = 0; i < 16; ++i) x[i] = rbf(x[i] * E.scale[ch + i]);
       }
       if (E.resid) {
-        const uint4 r0 = *reinterpret_cast<const uint4*>(E.resid + row_off + n);
-        const uint4 r1 = *reinterpret_cast<const uint4*>(E.resid + row_off + n + 8);
+        const uint4 r0 = *reinterpret_cast<const uint4*>(E.resid + res_off + n);
+        const uint4 r1 = *reinterpret_cast<const uint4*>(E.resid + res_off + n + 8);
         const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) { x[2 * i] = rbf(x[2 * i] + bf16lo(rr[i])); x[2 * i + 1] = rbf(x[2 * i + 1] + bf16hi(rr[i])); }
@@ -183,8 +185,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
         uint4 o0, o1;
         o0.x = pack_bf16(x[0], x[1]); o0.y = pack_bf16(x[2], x[3]); o0.z = pack_bf16(x[4], x[5]); o0.w = pack_bf16(x[6], x[7]);
         o1.x = pack_bf16(x[8], x[9]); o1.y = pack_bf16(x[10], x[11]); o1.z = pack_bf16(x[12], x[13]); o1.w = pack_bf16(x[14], x[15]);
-        *reinterpret_cast<uint4*>(E.out_raw + row_off + n) = o0;
-        *reinterpret_cast<uint4*>(E.out_raw + row_off + n + 8) = o1;
+        *reinterpret_cast<uint4*>(E.out_raw + raw_off + n) = o0;
+        *reinterpret_cast<uint4*>(E.out_raw + raw_off + n + 8) = o1;
       }
       if (E.out_act) {
         if (E.act == ACT_SWIGLU_BLK8) {
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
           }
           uint4 o;
           o.x = pack_bf16(y[0], y[1]); o.y = pack_bf16(y[2], y[3]); o.z = pack_bf16(y[4], y[5]); o.w = pack_bf16(y[6], y[7]);
-          *reinterpret_cast<uint4*>(E.out_act + ((size_t)b * p.T + m) * (size_t)(p.N / 2) + n / 2) = o;
+          *reinterpret_cast<uint4*>(E.out_act + (size_t)b * (size_t)p.act_bs + (size_t)m * (size_t)(p.N / 2) + n / 2) = o;
         } else if (E.act == ACT_SWIGLU_PAIR) {
           // columns (2i, 2i+1) = (gate_i, up_i)
           float y[8];
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
           }
           uint4 o;
           o.x = pack_bf16(y[0], y[1]); o.y = pack_bf16(y[2], y[3]); o.z = pack_bf16(y[4], y[5]); o.w = pack_bf16(y[6], y[7]);
-          *reinterpret_cast<uint4*>(E.out_act + ((size_t)b * p.T + m) * (size_t)(p.N / 2) + n / 2) = o;
+          *reinterpret_cast<uint4*>(E.out_act + (size_t)b * (size_t)p.act_bs + (size_t)m * (size_t)(p.N / 2) + n / 2) = o;
         } else {
           float y[16];
           if (E.act == ACT_SNAKE) {
@@ -227,8 +229,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
           uint4 o0, o1;
           o0.x = pack_bf16(y[0], y[1]); o0.y = pack_bf16(y[2], y[3]); o0.z = pack_bf16(y[4], y[5]); o0.w = pack_bf16(y[6], y[7]);
           o1.x = pack_bf16(y[8], y[9]); o1.y = pack_bf16(y[10], y[11]); o1.z = pack_bf16(y[12], y[13]); o1.w = pack_bf16(y[14], y[15]);
-          *reinterpret_cast<uint4*>(E.out_act + row_off + n) = o0;
-          *reinterpret_cast<uint4*>(E.out_act + row_off + n + 8) = o1;
+          *reinterpret_cast<uint4*>(E.out_act + act_off + n) = o0;
+          *reinterpret_cast<uint4*>(E.out_act + act_off + n + 8) = o1;
         }
       }
     }
@@ -262,6 +264,11 @@ int gemm_init() {
 
 int gemm_make_plan(GemmPlan* plan, const bf16* a, int B, int T, int K, int64_t lda, int64_t a_batch_stride, const bf16* w,
                    int N, int Kp, int ntaps, const int* shifts, int bn, const GemmEpilogue& ep) {
+  return gemm_make_plan_v(plan, a, B, T, K, lda, a_batch_stride, w, N, Kp, ntaps, shifts, bn, ep, GemmViews{});
+}
+
+int gemm_make_plan_v(GemmPlan* plan, const bf16* a, int B, int T, int K, int64_t lda, int64_t a_batch_stride, const bf16* w,
+                     int N, int Kp, int ntaps, const int* shifts, int bn, const GemmEpilogue& ep, const GemmViews& v) {
   Q3_REQUIRE(g_encode, "gemm_init() not called");
   Q3_REQUIRE(Kp % BK == 0 && Kp >= K, "Kp must be a multiple of 64 and >= K");
   Q3_REQUIRE(bn % 16 == 0 && bn >= 16 && bn <= 256, "bn must be a multiple of 16 in [16,256]");
@@ -270,9 +277,15 @@ int gemm_make_plan(GemmPlan* plan, const bf16* a, int B, int T, int K, int64_t l
   Q3_REQUIRE((lda * 2) % 16 == 0 && (a_batch_stride * 2) % 16 == 0 && ((uintptr_t)a % 16) == 0, "A alignment");
   memset(plan, 0, sizeof(*plan));
   plan->B = B; plan->T = T; plan->N = N; plan->Kp = Kp; plan->ntaps = ntaps; plan->bn = bn; plan->ep = ep;
+  const bool half = ep.act == ACT_SWIGLU_PAIR || ep.act == ACT_SWIGLU_BLK8;
+  plan->a_row0 = v.a_row0;
+  plan->raw_bs = v.raw_bs ? v.raw_bs : (long long)T * N;
+  plan->act_bs = v.act_bs ? v.act_bs : (long long)T * (half ? N / 2 : N);
+  plan->resid_bs = v.resid_bs ? v.resid_bs : (long long)T * N;
+  const int a_rows = v.a_rows ? v.a_rows : T;
   for (int i = 0; i < ntaps; ++i) plan->shift[i] = shifts[i];
   {
-    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)T, (cuuint64_t)B};
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)a_rows, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)lda * 2, (cuuint64_t)a_batch_stride * 2};
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BM, 1};
     cuuint32_t es[3] = {1, 1, 1};

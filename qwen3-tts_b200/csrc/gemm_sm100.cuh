@@ -27,13 +27,26 @@ struct GemmPlan {
   CUtensorMap tmA, tmW;
   int B, T, N, Kp, ntaps, bn;
   int shift[8];
+  int a_row0;                       // added to every A row coordinate (history-prefixed inputs of the streaming codec)
+  long long raw_bs, act_bs, resid_bs;  // batch strides (elements) of out_raw / out_act / resid; rows are N (N/2) wide
   GemmEpilogue ep;
+};
+
+// Views for tensors that are not a plain contiguous [B][T][*]: the A map may cover more rows than the T output rows
+// (a history prefix of a_row0 rows that the taps' negative shifts reach into), and every output / residual tensor
+// may sit inside a larger per-batch allocation.  0 strides mean "contiguous".
+struct GemmViews {
+  int a_rows = 0;       // rows of the A map per batch (0 -> T)
+  int a_row0 = 0;
+  long long raw_bs = 0, act_bs = 0, resid_bs = 0;
 };
 
 // Encode the two tensor maps for a problem (host).  a: [B][T][K] bf16 with row pitch lda (elements) and batch
 // stride (elements); w: [N][ntaps*Kp] bf16.  Returns 0 on success.
 int gemm_make_plan(GemmPlan* plan, const bf16* a, int B, int T, int K, int64_t lda, int64_t a_batch_stride,
                    const bf16* w, int N, int Kp, int ntaps, const int* shifts, int bn, const GemmEpilogue& ep);
+int gemm_make_plan_v(GemmPlan* plan, const bf16* a, int B, int T, int K, int64_t lda, int64_t a_batch_stride, const bf16* w,
+                     int N, int Kp, int ntaps, const int* shifts, int bn, const GemmEpilogue& ep, const GemmViews& v);
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
 int gemm_init();  // resolves cuTensorMapEncodeTiled, sets kernel attributes
 int gemm_pick_bn(int N, int mtiles, int B);  // largest tile width that still fills the 148 SMs

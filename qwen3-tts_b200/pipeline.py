@@ -55,18 +55,44 @@ class TTSEngine:
 
     @torch.no_grad()
     def stream_synthesize(self, inputs_embeds, trailing_text, tts_pad_embed, sp: SamplingParams, packet_frames: int = 4,
-                          left_context: int = 25):
+                          left_context="stateful"):
         """Streaming OUTPUT (new surface: the reference returns audio whole).  Yields, per packet of
         `packet_frames` frames (4 frames = 320 ms, Qwen3-TTS report §3.4), a list with one fp32 numpy waveform chunk per
-        row.  Each packet is decoded together with `left_context` already-emitted frames, exactly like the reference's
-        own chunked_decode does between chunks (…v2.py:886-896: 25 frames); `left_context=None` re-decodes the whole
-        prefix, which equals the one-shot causal decode bit for bit."""
+        row.  Default: the STATEFUL codec stream (q3_codec_stream_*) — each packet costs its own frames only and the
+        concatenated chunks equal the one-shot causal decode.  `left_context=25` decodes every packet together with 25
+        already-emitted frames, exactly like the reference's chunked_decode does between chunks (…v2.py:886-896);
+        `left_context=None` re-decodes the whole prefix."""
         dev = self.device
         emb = [e.to(dev, non_blocking=True) for e in inputs_embeds]
         tr = [t.to(dev, non_blocking=True) for t in trailing_text]
         pad = tts_pad_embed.to(dev, non_blocking=True)
-        hist = [torch.zeros(0, self.codec_cfg.num_quantizers, dtype=torch.int64, device=dev) for _ in emb]
+        K = self.codec_cfg.num_quantizers
         up = self.codec.total_upsample
+        B = len(emb)
+        if left_context == "stateful":
+            key = (B, int(packet_frames))
+            if getattr(self, "_cstream_key", None) != key:
+                if getattr(self, "_cstream", None) is not None:
+                    self._cstream.close()
+                self._cstream = self.codec.open_stream(B, max_packet_frames=int(packet_frames))
+                self._cstream_key = key
+            cs = self._cstream
+            cs.reset()
+            for pkt in self.ar.stream(emb, tr, pad, sp, packet_frames=packet_frames):
+                n_new = [int(p.shape[0]) for p in pkt]
+                n = max(n_new) if n_new else 0
+                if n == 0:
+                    yield [np.zeros(0, dtype=np.float32) for _ in pkt]
+                    continue
+                # rows that already finished (or got fewer frames) are padded with code 0: their state no longer matters
+                codes = torch.zeros(B, n, K, dtype=torch.int64, device=dev)
+                for b, p in enumerate(pkt):
+                    if p.shape[0]:
+                        codes[b, :p.shape[0]] = p
+                wav = cs.push(codes.transpose(1, 2).contiguous())[:, 0].to(torch.float32).cpu().numpy()
+                yield [wav[b, :n_new[b] * up] for b in range(B)]
+            return
+        hist = [torch.zeros(0, K, dtype=torch.int64, device=dev) for _ in emb]
         for pkt in self.ar.stream(emb, tr, pad, sp, packet_frames=packet_frames):
             out = [np.zeros(0, dtype=np.float32) for _ in pkt]
             # rows whose window has the same shape (the normal case: every live row got `packet_frames` new frames on top

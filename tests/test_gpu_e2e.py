@@ -80,7 +80,7 @@ def test_stream_synthesize_full_prefix_equals_one_shot_decode():
     pad = (torch.randn(H, generator=g) * 0.1).bfloat16()
     sp = q.SamplingParams(max_new_tokens=11, suppress_eos=True, seed=5)
     wavs, codes = eng.synthesize(embs, trail, pad, sp)
-    for lc in (None, 25):
+    for lc in ("stateful", None, 25):  # stateful codec stream (default), whole-prefix re-decode, the reference's 25-frame context
         parts = [[] for _ in embs]
         for pkt in eng.stream_synthesize(embs, trail, pad, sp, packet_frames=4, left_context=lc):
             for b, w in enumerate(pkt):

@@ -24,9 +24,9 @@ for f in range(N + 1):
     a, b = ref.record["talker_logits"][f], np.asarray(rb.record["talker_logits"][f], dtype=np.float32)
     s = a.std(); d = np.abs(a - b)
     print("talker frame", f, "max/std %.3f mean/std %.4f" % (d.max() / s, d.mean() / s), flush=True)
-worst = 0
+worst = wmean = 0
 for f in range(N):
     for j in range(G - 1):
         a, b = ref.record["cp_logits"][f * (G - 1) + j], np.asarray(rb.record["cp_logits"][f * (G - 1) + j], dtype=np.float32)
-        worst = max(worst, np.abs(a - b).max() / a.std())
-print("cp worst max/std %.3f" % worst)
+        worst = max(worst, np.abs(a - b).max() / a.std()); wmean = max(wmean, np.abs(a - b).mean() / a.std())
+print("cp worst max/std %.3f  worst mean/std %.4f" % (worst, wmean))
