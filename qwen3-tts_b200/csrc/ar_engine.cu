@@ -458,7 +458,7 @@ static int build_piece_table(q3_engine* e, const std::vector<Phase>& prog, int S
         m.ntc = (uint16_t)ntc;
         m.kb = (uint16_t)prog[i].kb;
         const size_t byte_off = (size_t)(reinterpret_cast<const char*>(prog[i].w) - e->wbase) + (size_t)t0 * prog[i].kb * 1024;
-        Q3_REQUIRE((byte_off >> 4) < ((size_t)1 << 32) && (byte_off & 1023) == 0, "weight offset out of range / unaligned");
+        Q3_REQUIRE((byte_off >> 4) < ((size_t)1 << 32) && (byte_off & 15) == 0, "weight offset out of range / unaligned");
         m.woff16 = (uint32_t)(byte_off >> 4);
       }
       meta[i] = m;
