@@ -515,8 +515,8 @@ static int make_smem_plan(q3_engine* e, std::vector<Phase>& prog, int B, int nt,
   int slot_cap = MAX_SLOTS;
   if (const char* f = getenv("Q3_RING_SLOTS")) slot_cap = std::max(2, std::min(MAX_SLOTS, atoi(f)));
   pl.slot_blocks = 0;
-  int sb_first = 4;
-  if (const char* f = getenv("Q3_SLOT_BLOCKS")) sb_first = std::max(1, std::min(4, atoi(f)));
+  int sb_first = nt == 4 ? 2 : 4;  // the largest batch class keeps its B fragments of a piece in registers: 2-block pieces
+  if (const char* f = getenv("Q3_SLOT_BLOCKS")) sb_first = std::max(1, std::min(sb_first, atoi(f)));
   for (int sb : {sb_first, 2, 1}) {
     const int r = avail / (NWARPS * sb * 1024);
     if (r >= 2) { pl.slot_blocks = sb; pl.nslots = std::min(r, slot_cap); break; }

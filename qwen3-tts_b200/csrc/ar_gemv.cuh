@@ -301,16 +301,16 @@ __device__ __forceinline__ int idiv_small(int a, int b) {  // exact for 0 <= a <
   return __float2int_rz(__fdividef((float)a + 0.5f, (float)b));
 }
 
-// One full ring piece (4 k32-blocks of one tile): A fragments from the ring slot, B fragments already in registers.
+// One full ring piece (NBLK = 4 or 2 k32-blocks of one tile): A fragments from the ring slot, B fragments already in registers.
 // A block is two 512-byte halves; lane l's 16 bytes of a half ARE the four A registers of one m16n8k16 MMA
 // (pack_weight_kernel), so no register shuffling sits between the loads and the tensor pipe.
-template <int NT, int NACC>
-__device__ __forceinline__ void piece4(float (&acc)[NACC][NT][4], uint32_t sp, const uint4 (&b)[4][NT], int nct) {
-  uint4 a1[4], a2[4];
+template <int NT, int NACC, int NBLK>
+__device__ __forceinline__ void piece_full(float (&acc)[NACC][NT][4], uint32_t sp, const uint4 (&b)[(NT == 4 ? 2 : 4)][NT], int nct) {
+  uint4 a1[NBLK], a2[NBLK];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { a1[i] = lds128(sp + i * 1024); a2[i] = lds128(sp + i * 1024 + 512); }
+  for (int i = 0; i < NBLK; ++i) { a1[i] = lds128(sp + i * 1024); a2[i] = lds128(sp + i * 1024 + 512); }
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < NBLK; ++i)
 #pragma unroll
     for (int n = 0; n < NT; ++n)
       if (n < nct) {
@@ -319,13 +319,13 @@ __device__ __forceinline__ void piece4(float (&acc)[NACC][NT][4], uint32_t sp, c
       }
 }
 
-// B fragments of 4 consecutive k-blocks starting at block kb0 (wrapping at KB) straight from global memory.
+// B fragments of PB (4; 2 at the largest batch class, whose ring pieces are 2 blocks) consecutive k-blocks starting at block kb0 (wrapping at KB) straight from global memory.
 // gsrc points at this lane's column g / k offset t*8; `rows_left` = nc - g (columns n*8+g beyond it read zero).
 template <int NT>
-__device__ __forceinline__ void load_bfrags(uint4 (&dst)[4][NT], const bf16* __restrict__ gsrc, int src_ld, int rows_left, int nct,
-                                            int kb0, int KB) {
+__device__ __forceinline__ void load_bfrags(uint4 (&dst)[(NT == 4 ? 2 : 4)][NT], const bf16* __restrict__ gsrc, int src_ld, int rows_left,
+                                            int nct, int kb0, int KB) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < (NT == 4 ? 2 : 4); ++i) {
     int kk = kb0 + i;
     if (kk >= KB) kk -= KB;
 #pragma unroll
@@ -459,12 +459,13 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
       // Un-staged inputs (K too large for the x area: the down projections): B fragments come straight from L2 into
       // registers, one piece AHEAD of the MMAs that use them, so only the first piece of a run exposes the L2 latency
       const bf16* gsrc = src + (size_t)g * src_ld + t * 8;
-      uint4 bq[4][NT], bnx[4][NT];
+      constexpr int PB = NT == 4 ? 2 : 4;  // blocks per ring piece (the plan never gives the largest batch class more)
+      uint4 bq[PB][NT], bnx[PB][NT];
       if (!staged) load_bfrags<NT>(bq, gsrc, src_ld, nc - g, nct, kbi, KB);
 #pragma unroll 1
       while (u < rgm.u1) {
         const int nb = q3ring::imin(rg.SB, rgm.u1 - u);
-        const bool full = nb == 4 && kbi + 4 <= KB;  // every shipped shape: runs and tiles are multiples of 4 blocks
+        const bool full = nb == rg.SB && (nb == PB || nb == 2) && kbi + nb <= KB;  // every shipped shape: runs and tiles are multiples of 4 blocks
         if (!staged && u + nb < rgm.u1) {
           int kn = kbi + nb;
           if (kn >= KB) kn -= KB;
@@ -484,13 +485,16 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
           if (staged) {
             const uint32_t xb = xb0 + (uint32_t)kbi * 64u;
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < PB; ++i)
 #pragma unroll
               for (int n = 0; n < NT; ++n)
-                if (n < nct) bq[i][n] = lds128(xb + (uint32_t)(i * 64 + n * 8 * xstride));
+                if (i < nb && n < nct) bq[i][n] = lds128(xb + (uint32_t)(i * 64 + n * 8 * xstride));
           }
-          if (!(P.flags & 16)) piece4<NT, NACC>(acc, sp, bq, nct);  // (flag 16: experiment, skip the tensor work)
-          kbi += 4;
+          if (!(P.flags & 16)) {  // (flag 16: experiment, skip the tensor work)
+            if (PB == 4 && nb == 4) piece_full<NT, NACC, PB>(acc, sp, bq, nct);
+            else piece_full<NT, NACC, 2>(acc, sp, bq, nct);
+          }
+          kbi += nb;
         } else {
           // general path (tiny test shapes, a tile boundary inside the piece): one block at a time, rolled
 #pragma unroll 1
@@ -521,7 +525,7 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
         ring_release(rg, P, lane, policy);
         if (!staged) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < PB; ++i)
 #pragma unroll
             for (int n = 0; n < NT; ++n) bq[i][n] = bnx[i][n];
         }
