@@ -115,6 +115,10 @@ int q3_session_begin(q3_engine* e, int32_t n_slots, int32_t max_trailing, const 
 int q3_admit(q3_engine* e, int32_t n, const int32_t* slots_host, const uint32_t* keys_host, const void* embeds_dev,
              const int32_t* lens_host, const void* trailing_dev, const int32_t* trailing_lens_host,
              int32_t trailing_stride, void* stream);
+/* Streaming text input: append n rows [n][H] bf16 to the trailing_text_hidden of a running row (static batch or session);
+ * frame t adds trailing[t] while t < the row's trailing length and tts_pad afterwards (modeling_qwen3_tts.py:1689-1692).
+ * The capacity is the trailing stride given at q3_prefill / max_trailing of q3_session_begin. */
+int q3_append_trailing(q3_engine* e, int32_t slot, const void* rows_dev, int32_t n, void* stream);
 /* give up rows that reached their frame horizon without EOS (their slots become free) */
 int q3_release_slots(q3_engine* e, int32_t n, const int32_t* slots_host, void* stream);
 

@@ -941,6 +941,22 @@ extern "C" int q3_decode(q3_engine* e, int32_t max_frames, int32_t* codes_dev, i
   return launch_program(e, e->off_frame, (int)e->prog_frame.size(), 1, max_frames, e->nt_frame, e->plan_frame, e->pt_frame, codes_dev, stream);
 }
 
+// Streaming TEXT input: more trailing_text_hidden rows for a row that is already generating.  Frame t of a
+// row adds trailing[t] while t < its trailing length and tts_pad afterwards (modeling_qwen3_tts.py:1689-1692), so rows
+// appended before the frame that needs them are indistinguishable from rows given at prefill.
+extern "C" int q3_append_trailing(q3_engine* e, int32_t slot, const void* rows_dev, int32_t n, void* stream_) {
+  Q3_REQUIRE(e && e->B > 0 && rows_dev && n >= 1, "bad argument");
+  Q3_REQUIRE(slot >= 0 && slot < e->B, "slot %d out of range", slot);
+  Q3_REQUIRE(e->trailing && e->trailing_len[slot] + n <= e->trailing_cap, "trailing text of row %d would exceed its capacity %d", slot,
+             e->trailing_cap);
+  Q3_CUDA(cudaSetDevice(e->cfg.device));
+  const int H = e->cfg.talker.hidden_size;
+  Q3_CUDA(cudaMemcpyAsync(e->trailing + ((size_t)slot * e->trailing_cap + e->trailing_len[slot]) * H, rows_dev, (size_t)n * H * 2,
+                          cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
+  e->trailing_len[slot] += n;
+  return 0;
+}
+
 extern "C" int q3_release_slots(q3_engine* e, int32_t n, const int32_t* slots_host, void* stream_) {
   Q3_REQUIRE(e && e->session && slots_host && n >= 0 && n <= MAXB, "bad argument");
   Q3_CUDA(cudaSetDevice(e->cfg.device));

@@ -399,10 +399,7 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
     }
   }
   PROF_MARK(2);
-  if (ntc <= 0) {
-    cta_sync();
-    return xpar;
-  }
+  if (ntc <= 0) return xpar;  // (the phase loop syncs the CTA right after the body)
 
   const bool swiglu = epi == EPI_SWIGLU;
   const int rsh = swiglu ? 3 : 4;  // output rows per tile: 8 (gate/up pairs) or 16
@@ -573,8 +570,7 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
     }
     PROF_MARK(4);
   }
-  cta_sync();
-  return xpar;
+  return xpar;  // (the phase loop syncs the CTA right after the body)
 }
 
 }  // namespace

@@ -59,6 +59,143 @@ __device__ __noinline__ float kth_largest(const float* sv, int V, int k, unsigne
   return __uint_as_float(u);
 }
 
+// Fast path of the default sampling configuration (top-k with k <= 128, no top-p): exact top-k threshold from ONE
+// histogram pass over a monotone 2048-bin key of (score - max) plus a rank count among the few scores of the
+// threshold bin, then softmax + inverse CDF over the <= 384 kept scores in token-id order.  ~10 CTA syncs instead of
+// the ~30 of the generic path (4-pass radix select + full-vocabulary scan); returns false (nothing decided) when a
+// degenerate input (hundreds of ties, fewer than k finite scores) needs the generic path.
+__device__ __noinline__ bool sample_fast(const float* sv, int V, int k, float u, float* scratch, float* red, int* ired, int* tok_out) {
+  int* hist = reinterpret_cast<int*>(scratch);                      // [2048]
+  float* cand = scratch + 2048;                                     // [256]
+  int* kidx = reinterpret_cast<int*>(scratch + 2048 + 256);         // [384]
+  float* kp = scratch + 2048 + 256 + 384;                           // [384]
+  int* sidx = reinterpret_cast<int*>(scratch + 2048 + 256 + 768);   // [384]
+  float* spp = scratch + 2048 + 256 + 1152;                         // [384]
+  __shared__ int s_misc[8];  // 0 threshold bin, 1 rank inside it, 2 #candidates, 3 #kept, 4 threshold bits, 5 token
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int i = tid; i < V; i += NTHREADS) mx = fmaxf(mx, sv[i]);
+  mx = block_reduce(mx, red, 0);
+#pragma unroll 1
+  for (int i = tid; i < 2048; i += NTHREADS) hist[i] = 0;
+  if (tid == 0) { s_misc[0] = -1; s_misc[2] = 0; s_misc[3] = 0; s_misc[4] = __float_as_int(-INFINITY); }
+  cta_sync();
+  const float lo = mx - 32.f;
+#pragma unroll 1
+  for (int i = tid; i < V; i += NTHREADS) {
+    const float sc = sv[i];
+    if (sc > -INFINITY) atomicAdd(&hist[min(2047, max(0, (int)((sc - lo) * 64.f)))], 1);
+  }
+  cta_sync();
+  // thread t owns bins [8t, 8t+8); scores in a higher bin are strictly larger
+  int hb[8], S = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { hb[j] = hist[8 * tid + j]; S += hb[j]; }
+  int incl = S;  // inclusive SUFFIX sum inside the warp (threads above me own larger scores)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int n = __shfl_down_sync(0xffffffffu, incl, o);
+    if (lane + o < 32) incl += n;
+  }
+  if (lane == 0) ired[wp] = incl;
+  cta_sync();
+  int above = incl - S;
+#pragma unroll 1
+  for (int w = wp + 1; w < NWARPS; ++w) above += ired[w];
+  {
+    int run = above;
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+      if (run < k && k <= run + hb[j]) { s_misc[0] = 8 * tid + j; s_misc[1] = k - run; }
+      run += hb[j];
+    }
+  }
+  cta_sync();
+  const int tb = s_misc[0], kk = s_misc[1];
+  if (tb < 0) return false;  // fewer than k finite scores
+#pragma unroll 1
+  for (int i = tid; i < V; i += NTHREADS) {
+    const float sc = sv[i];
+    if (sc > -INFINITY && min(2047, max(0, (int)((sc - lo) * 64.f))) == tb) {
+      const int p = atomicAdd(&s_misc[2], 1);
+      if (p < 256) cand[p] = sc;
+    }
+  }
+  cta_sync();
+  const int nc = s_misc[2];
+  if (nc > 256) return false;
+  if (tid < nc) {
+    const float v = cand[tid];
+    int gt = 0, ge = 0;
+#pragma unroll 1
+    for (int j = 0; j < nc; ++j) { const float w = cand[j]; gt += w > v; ge += w >= v; }
+    if (gt < kk && kk <= ge) s_misc[4] = __float_as_int(v);  // (ties write the same value)
+  }
+  cta_sync();
+  const float thr = __int_as_float(s_misc[4]);
+  // kept set (HF keeps everything >= the k-th largest: ties at the threshold stay)
+#pragma unroll 1
+  for (int i = tid; i < V; i += NTHREADS) {
+    const float sc = sv[i];
+    if (sc > -INFINITY && sc >= thr) {
+      const int p = atomicAdd(&s_misc[3], 1);
+      if (p < 384) { kidx[p] = i; kp[p] = __expf(sc - mx); }
+    }
+  }
+  cta_sync();
+  const int m = s_misc[3];
+  if (m > 384 || m == 0) return false;
+  // token-id order by rank counting (the arrival order of the atomics is not deterministic, the ids are)
+#pragma unroll 1
+  for (int e = tid; e < m; e += NTHREADS) {
+    const int id = kidx[e];
+    int r = 0;
+#pragma unroll 1
+    for (int j = 0; j < m; ++j) r += kidx[j] < id;
+    sidx[r] = id;
+    spp[r] = kp[e];
+  }
+  cta_sync();
+  if (tid < 32) {  // inverse CDF over the sorted kept set
+    const int per = (m + 31) >> 5;
+    const int a = min(m, lane * per), bnd = min(m, a + per);
+    float loc = 0.f;
+#pragma unroll 1
+    for (int j = a; j < bnd; ++j) loc += spp[j];
+    float inc = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    const float total = __shfl_sync(0xffffffffu, inc, 31);
+    const float target = u * total;
+    float run = inc - loc;
+    int cnd = 0x7fffffff;
+#pragma unroll 1
+    for (int j = a; j < bnd; ++j) {
+      run += spp[j];
+      if (run > target && cnd == 0x7fffffff && spp[j] > 0.f) cnd = j;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnd = min(cnd, __shfl_xor_sync(0xffffffffu, cnd, o));
+    if (cnd == 0x7fffffff) {  // rounding pushed the target past the last partial sum: take the last token with p > 0
+      int last = -1;
+#pragma unroll 1
+      for (int j = a; j < bnd; ++j)
+        if (spp[j] > 0.f) last = j;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+      cnd = max(last, 0);
+    }
+    if (lane == 0) s_misc[5] = sidx[cnd];
+  }
+  cta_sync();
+  *tok_out = s_misc[5];
+  return true;
+}
+
 __device__ __forceinline__ void sample_phase(const Phase& ph, const KParams& P, unsigned char* smem, int frame, bool in_prefill) {
   const int b = blockIdx.x;
   DevState* st = P.st;
@@ -126,6 +263,9 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, const KParams& P, 
     for (int i = tid; i < V; i += NTHREADS)
       if (sv[i] == mx) idx = min(idx, i);
     tok = block_min_int(idx, ired);
+  } else if (top_p >= 1.0f && top_k > 0 && top_k < V && top_k <= 128 &&
+             sample_fast(sv, V, top_k, philox_uniform(P.sp.seed, P.row_key[b], (uint32_t)fidx, (uint32_t)group), pv, red, ired, &tok)) {
+    // (decided by the fast path)
   } else {
     if (top_k > 0 && top_k < V) {
       const float thr = kth_largest(sv, V, top_k, hist, ired);

@@ -122,14 +122,15 @@ class AREngine:
         return s
 
     def prefill(self, inputs_embeds: Sequence[torch.Tensor], trailing_text: Sequence[torch.Tensor],
-                tts_pad_embed: torch.Tensor, sp: SamplingParams):
+                tts_pad_embed: torch.Tensor, sp: SamplingParams, trailing_capacity: int = 0):
+        """`trailing_capacity` > longest trailing text reserves room for append_trailing() (streaming text input)."""
         B = len(inputs_embeds)
         H = self.cfg.talker.hidden_size
         dev = self.device
         emb = torch.cat([e.reshape(-1, H) for e in inputs_embeds], 0).to(dev, torch.bfloat16).contiguous()
         lens = (C.c_int32 * B)(*[int(e.reshape(-1, H).shape[0]) for e in inputs_embeds])
         tl = [int(t.reshape(-1, H).shape[0]) for t in trailing_text]
-        Tt = max(tl) if tl else 0
+        Tt = max(max(tl) if tl else 0, int(trailing_capacity))
         pad = tts_pad_embed.reshape(H).to(dev, torch.bfloat16).contiguous()
         if Tt > 0:
             tr = pad.expand(B, Tt, H).clone()
@@ -180,6 +181,14 @@ class AREngine:
         self._hold = self._hold + (emb, tr)
         _lib.check(self.lib.q3_admit(self.h, n, (C.c_int32 * n)(*[int(x) for x in slots]), (C.c_uint32 * n)(*[int(k) & 0xffffffff for k in keys]),
                                      emb.data_ptr(), lens, trp, (C.c_int32 * n)(*tl), Tt, C.c_void_p(stream)))
+
+    def append_trailing(self, slot: int, rows: torch.Tensor):
+        """Streaming text input: more trailing_text_hidden rows (n, H) for a row that is already generating."""
+        H = self.cfg.talker.hidden_size
+        r = rows.reshape(-1, H).to(self.device, torch.bfloat16).contiguous()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self._hold = self._hold + (r,)
+        _lib.check(self.lib.q3_append_trailing(self.h, int(slot), r.data_ptr(), int(r.shape[0]), C.c_void_p(stream)))
 
     def release_slots(self, slots: Sequence[int]):
         n = len(slots)

@@ -75,3 +75,28 @@ def test_eos_frees_the_slot_and_trims():
         assert c.shape[1] == cfg.num_code_groups and 0 <= c.shape[0] <= 40
         assert (c[:, 0] != cfg.codec_eos_token_id).all()  # the EOS frame itself is dropped
     eng.close()
+
+
+def test_streaming_text_input_equals_text_given_up_front():
+    """trailing_text_hidden rows appended while the row is generating (before the frame that consumes them) give the
+    same codes as the whole text at prefill (modeling_qwen3_tts.py:1689-1692: frame t adds trailing[t], then tts_pad)."""
+    import qwen3_tts_b200 as q
+    cfg, eng, embs, trail, pad = _setup()
+    H = cfg.talker.hidden_size
+    g = torch.Generator().manual_seed(3)
+    trail = [(torch.randn(7, H, generator=g) * 0.1).bfloat16(), (torch.randn(5, H, generator=g) * 0.1).bfloat16()]
+    sp = q.SamplingParams(do_sample=True, max_new_tokens=11, suppress_eos=True, seed=9)
+    ref = [c.cpu().numpy() for c in eng.generate(embs[:2], trail, pad, sp)]
+    eng.prefill(embs[:2], [t[:2] for t in trail], pad, sp, trailing_capacity=16)
+    codes = torch.zeros(2, 10, cfg.num_code_groups, dtype=torch.int32, device=DEV)
+    eng.decode(2, codes)                      # frames 0 and 1 consume the two rows given at prefill
+    eng.append_trailing(0, trail[0][2:4])
+    eng.append_trailing(1, trail[1][2:])
+    eng.decode(2, codes)
+    eng.append_trailing(0, trail[0][4:])
+    eng.decode(6, codes)
+    torch.cuda.synchronize()
+    got = codes.cpu().numpy()
+    for b in range(2):
+        assert (got[b] == ref[b]).all(), f"row {b} differs at {np.argwhere(got[b] != ref[b])[0]}"
+    eng.close()
