@@ -26,10 +26,18 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# NCCL's communicator / topology lines are wanted (the driver reads them), stdout must stay the single JSON line:
-# INFO level, written to stderr
+# NCCL's communicator / topology lines are wanted (the driver reads them) but stdout must stay the single JSON line:
+# NCCL logs at INFO level to file descriptor 1, so fd 1 is pointed at stderr for everything except the result line,
+# which is written to a private duplicate of the real stdout.
 os.environ.setdefault("NCCL_DEBUG", "INFO")
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _RESULT_OUT.write(json.dumps(obj) + "\n")
+    _RESULT_OUT.flush()
+
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -401,7 +409,7 @@ def main():
                                 "frames_per_step": n, **det},
                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "gpu_launches": 0, "wall_s": time.perf_counter() - t_begin, "build_s": t_build}
-        print(json.dumps(out), flush=True)
+        emit(out)
         return
 
     # ------------------------------------------------------------------ B200 arm
@@ -618,8 +626,7 @@ def main():
             except Exception as e:  # the headline line must survive whatever happens here
                 out["extras"][name] = {"error": repr(e)[:200]}
     if rank == 0:
-        sys.stdout.flush()
-        print(json.dumps(out), flush=True)
+        emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -127,6 +127,11 @@ int q3_release_slots(q3_engine* e, int32_t n, const int32_t* slots_host, void* s
  * finished[b] = 1 once row b sampled EOS.  Host pointers (may be NULL). */
 int q3_get_progress(q3_engine* e, int32_t* frames_done, int32_t* n_valid, int32_t* finished);
 
+/* Per-step hidden states = the second return value of generate() (modeling_qwen3_tts.py:2281: the last layer's normed
+ * output of the newest position of every step): hid_dev bf16 [B][stride][hidden] gets row b's step s at [b][s][:]
+ * (s = 0 is the prefill).  NULL disables the capture.  Call before q3_prefill. */
+int q3_set_hidden_capture(q3_engine* e, void* hid_dev, int32_t stride);
+
 /* Test hooks (used by tests/ only): teacher forcing and raw-logit capture.
  * forced: int32 [B][n_frames][G] device (or NULL to disable); talker_logits: fp32 [n_frames+1][B][V];
  * cp_logits: fp32 [n_frames][G-1][B][Vc].  Pointers must stay valid until cleared. */

@@ -61,7 +61,7 @@ class SpkCfg(C.Structure):
 AR_SYMBOLS = ["q3_abi_version", "q3_last_error", "q3_engine_create", "q3_engine_destroy", "q3_engine_load_tensor",
               "q3_engine_finalize", "q3_prefill", "q3_decode", "q3_get_progress", "q3_set_debug",
               "q3_algorithmic_bytes", "q3_set_profile", "q3_describe_frame_program", "q3_debug_time_phases", "q3_debug_set_skip",
-              "q3_session_begin", "q3_admit", "q3_release_slots", "q3_append_trailing"]
+              "q3_session_begin", "q3_admit", "q3_release_slots", "q3_append_trailing", "q3_set_hidden_capture"]
 CODEC_SYMBOLS = ["q3_codec_create", "q3_codec_destroy", "q3_codec_load_tensor", "q3_codec_finalize",
                  "q3_codec_forward", "q3_codec_total_upsample", "q3_codec_last_launch_count",
                  "q3_codec_stream_open", "q3_codec_stream_step", "q3_codec_stream_reset", "q3_codec_stream_position", "q3_codec_stream_close",
@@ -110,6 +110,7 @@ def load():
     lib.q3_session_begin.argtypes = [vp, i32, i32, vp, C.POINTER(Sampling), vp]
     lib.q3_release_slots.argtypes = [vp, i32, C.POINTER(i32), vp]
     lib.q3_append_trailing.argtypes = [vp, i32, vp, i32, vp]
+    lib.q3_set_hidden_capture.argtypes = [vp, vp, i32]
     lib.q3_admit.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(C.c_uint32), vp, C.POINTER(i32), vp, C.POINTER(i32), i32, vp]
     lib.q3_get_progress.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     lib.q3_set_debug.argtypes = [vp, vp, i32, vp, vp]

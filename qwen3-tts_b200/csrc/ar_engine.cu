@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) q3_step_kernel(const __grid_co
         PROF_MARK(6);
       }
       const int type = ph.type;
-      if (type == PH_GEMV) xpar = gemv_phase<NT>(ph, meta[pi], P, rg, smem, &s_tab, xbar, xpar, policy);
+      if (type == PH_GEMV) xpar = gemv_phase<NT>(ph, meta[pi], P, rg, smem, &s_tab, xbar, xpar, policy, frame);
       else if (type == PH_ATTN) attn_phase(ph, P, smem + P.plan.x_off, frame);
       else sample_phase(ph, P, smem + P.plan.x_off, frame, P.mode == 0);
       if (dhave) reinterpret_cast<uint32_t*>(&s_ph[slot ^ 1])[tid] = dreg;
@@ -243,6 +243,8 @@ struct q3_engine {
   int B = 0;
   int codes_stride = 0;
   const int* forced = nullptr;
+  bf16* hid_out = nullptr;
+  int hid_stride = 0;
   int n_forced = 0;
   float *dbg_t = nullptr, *dbg_c = nullptr;
   unsigned long long* prof = nullptr;
@@ -732,6 +734,7 @@ static int launch_program(q3_engine* e, int off, int n, int mode, int max_iters,
   P.tts_pad = e->tts_pad; P.seen = e->seen; P.codes_out = codes_dev; P.codes_stride = e->codes_stride;
   P.split_buf = e->split_buf; P.forced = e->forced; P.n_forced = e->n_forced; P.dbg_tlogits = e->dbg_t; P.dbg_clogits = e->dbg_c; P.prof = (mode == 1) ? e->prof : nullptr;
   P.flags = e->flags; P.wbase = e->wbase; P.keep_fraction = e->keep_fraction;
+  P.hid_out = e->hid_out; P.hid_stride = e->hid_stride;
   P.runs = pt.runs; P.run_off = pt.off;
   P.plan = plan; P.cp_phases = (off == e->off_frame && n == (int)e->prog_frame.size()) ? e->cp_phases : 0;
   Q3_REQUIRE(n <= MAX_PHASES, "program of %d phases exceeds %d", n, MAX_PHASES);
@@ -991,6 +994,16 @@ extern "C" int q3_set_debug(q3_engine* e, const int32_t* forced_dev, int32_t n_f
   Q3_REQUIRE(e, "null engine");
   e->forced = forced_dev; e->n_forced = forced_dev ? n_frames : 0;
   e->dbg_t = talker_logits_dev; e->dbg_c = cp_logits_dev;
+  return 0;
+}
+
+// Per-step hidden states (the second return value of Qwen3TTSForConditionalGeneration.generate, :2281): hid_dev bf16
+// [B][stride][H] receives, for row b, the final-norm output of its last position at step s (s = 0: the prefill) at
+// [b][s][:].  NULL disables.  Set before q3_prefill.
+extern "C" int q3_set_hidden_capture(q3_engine* e, void* hid_dev, int32_t stride) {
+  Q3_REQUIRE(e, "null engine");
+  e->hid_out = reinterpret_cast<bf16*>(hid_dev);
+  e->hid_stride = hid_dev ? stride : 0;
   return 0;
 }
 

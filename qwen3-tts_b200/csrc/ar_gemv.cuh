@@ -251,13 +251,18 @@ __device__ __forceinline__ uint32_t norm_pair(uint32_t x2, uint32_t w2, float in
 // result is written to smem once.  The norm weights sit in nw_s (fetched before the preceding grid barrier).
 // (Un-normed inputs are copied by the TMA unit, see gemv_phase.)  K <= 2048.
 __device__ __forceinline__ void stage_columns(const bf16* __restrict__ src, int src_ld, float eps, bf16* __restrict__ save, unsigned int save_mask,
-                                              int K, int nc, char* __restrict__ xs, int xstride, const uint4* __restrict__ nw_s) {
+                                              int K, int nc, char* __restrict__ xs, int xstride, const uint4* __restrict__ nw_s,
+                                              bf16* __restrict__ hid, int hid_stride, int hid_step, const int* __restrict__ frame0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nv = K >> 3;
 #pragma unroll 1
   for (int col = warp; col < nc; col += NWARPS) {
     const uint4* xr = reinterpret_cast<const uint4*>(src + (size_t)col * src_ld);
     uint4* drow = reinterpret_cast<uint4*>(xs + (size_t)col * xstride);
+    // per-step hidden-state capture: row `col`, its own step index (prefill = 0, frame f -> f + 1 - frame0)
+    const int hstep = hid ? hid_step - frame0[col] : -1;
+    uint4* hrow = (hid && save && ((save_mask >> col) & 1u) && hstep >= 0 && hstep < hid_stride)
+                      ? reinterpret_cast<uint4*>(hid + ((size_t)col * hid_stride + hstep) * K) : nullptr;
     uint4 v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -285,6 +290,7 @@ __device__ __forceinline__ void stage_columns(const bf16* __restrict__ src, int 
         o.z = norm_pair(v[i].z, w.z, inv);
         o.w = norm_pair(v[i].w, w.w, inv);
         if (save && ((save_mask >> col) & 1u)) reinterpret_cast<uint4*>(save + (size_t)col * K)[lane + 32 * i] = o;
+        if (hrow) hrow[lane + 32 * i] = o;
         drow[lane + 32 * i] = o;
       }
     }
@@ -360,7 +366,7 @@ __device__ __forceinline__ void flush_acc(float (&acc)[NACC][NT][4], float* pp, 
 // The phase body.  `m` is this CTA's meta of the phase (tiles owned, K blocks); the weights arrive through the ring.
 template <int NT>
 __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, const KParams& P, Ring& rg, unsigned char* smem,
-                                               RoundTab* tab, uint32_t xbar, uint32_t xpar, uint64_t policy) {
+                                               RoundTab* tab, uint32_t xbar, uint32_t xpar, uint64_t policy, int frame) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int KB = m.kb, K = KB * 32, epi = ph.epi, ntc = m.ntc;
@@ -384,7 +390,8 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
   // ---- activations -> shared memory
   if (staged && (ntc > 0 || save) && !(P.flags & 32)) {
     if (normed) {
-      stage_columns(src, src_ld, ph.eps, save, P.mode == 0 ? P.admit_mask : 0xffffffffu, K, nc, xs, xstride, nw_s);
+      stage_columns(src, src_ld, ph.eps, save, P.mode == 0 ? P.admit_mask : 0xffffffffu, K, nc, xs, xstride, nw_s,
+                    save ? P.hid_out : nullptr, P.hid_stride, P.mode == 0 ? 0 : frame + 1, P.frame0);
     } else {
       // plain copy of nc contiguous rows: one bulk (TMA) copy per column, completion on the CTA's x barrier
       if (tid == 0) {

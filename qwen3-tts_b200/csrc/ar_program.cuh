@@ -125,6 +125,8 @@ struct KParams {
   int* codes_out;           // [B][codes_stride][G]
   int codes_stride;
   float* split_buf;         // [MAXB*nkv*MAXSPLIT][RMAX][130]
+  bf16* hid_out;            // optional [B][hid_stride][H]: the normed last hidden state of every step (generate()'s 2nd return)
+  int hid_stride;
   // debug hooks
   const int* forced;
   int n_forced;

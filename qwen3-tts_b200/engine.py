@@ -259,19 +259,32 @@ class AREngine:
         return want
 
     @torch.no_grad()
-    def generate(self, inputs_embeds, trailing_text, tts_pad_embed, sp: SamplingParams) -> List[torch.Tensor]:
+    def generate(self, inputs_embeds, trailing_text, tts_pad_embed, sp: SamplingParams, return_hidden: bool = False):
         """Returns per-row LongTensor (N_i, G) trimmed at the first EOS (modeling_qwen3_tts.py:2283-2290).
-        HF emits max_new_tokens-1 complete frames when no EOS is sampled."""
+        HF emits max_new_tokens-1 complete frames when no EOS is sampled.  With return_hidden also the per-step
+        hidden states (N_i, H) of :2281/:2290 (the reference's second return value)."""
         B = len(inputs_embeds)
         G = self.cfg.num_code_groups
+        H = self.cfg.talker.hidden_size
         max_frames = self._frame_budget(inputs_embeds, sp)
-        self.prefill(inputs_embeds, trailing_text, tts_pad_embed, sp)
-        codes = torch.zeros(B, max(max_frames, 1), G, dtype=torch.int32, device=self.device)
-        if max_frames > 0:
-            self.decode(max_frames, codes)
-        torch.cuda.current_stream(self.device).synchronize()
+        hid = None
+        if return_hidden:
+            hid = torch.zeros(B, max(max_frames, 1) + 1, H, dtype=torch.bfloat16, device=self.device)
+            _lib.check(self.lib.q3_set_hidden_capture(self.h, hid.data_ptr(), hid.shape[1]))
+        try:
+            self.prefill(inputs_embeds, trailing_text, tts_pad_embed, sp)
+            codes = torch.zeros(B, max(max_frames, 1), G, dtype=torch.int32, device=self.device)
+            if max_frames > 0:
+                self.decode(max_frames, codes)
+            torch.cuda.current_stream(self.device).synchronize()
+        finally:
+            if return_hidden:
+                _lib.check(self.lib.q3_set_hidden_capture(self.h, None, 0))
         _, n_valid, _ = self.progress()
-        return [codes[b, :min(n_valid[b], max_frames)].to(torch.int64) for b in range(B)]
+        out = [codes[b, :min(n_valid[b], max_frames)].to(torch.int64) for b in range(B)]
+        if return_hidden:
+            return out, [hid[b, :o.shape[0]].clone() for b, o in enumerate(out)]
+        return out
 
     @torch.no_grad()
     def stream(self, inputs_embeds, trailing_text, tts_pad_embed, sp: SamplingParams,

@@ -202,8 +202,8 @@ class Qwen3TTSForConditionalGenerationB200:
                  top_k: int = 50, top_p: float = 1.0, temperature: float = 0.9, subtalker_dosample: bool = True,
                  subtalker_top_k: int = 50, subtalker_top_p: float = 1.0, subtalker_temperature: float = 0.9,
                  eos_token_id: Optional[int] = None, repetition_penalty: float = 1.05, seed: Optional[int] = None, **kwargs):
-        """Signature and return of :2022-2043 / :2292.  The second return value (per-step hidden states) is not
-        produced by the fused engine; the reference's own wrappers discard it."""
+        """Signature and return of :2022-2043 / :2292: (codes list, per-step hidden-state list).  The reference's own
+        wrappers discard the second value; it is captured by the head phase of the fused kernel."""
         embeds, trailing, pad = self.build_prefill(input_ids, instruct_ids, ref_ids, voice_clone_prompt, languages,
                                                    speakers, non_streaming_mode)
         if eos_token_id is not None and eos_token_id != self.cfg.codec_eos_token_id:
@@ -219,13 +219,16 @@ class Qwen3TTSForConditionalGenerationB200:
                             seed=seed)
         tr = trailing
         out: List[torch.Tensor] = []
+        hids: List[torch.Tensor] = []
         mb = self.engine.max_batch
         for s in range(0, len(embeds), mb):  # the reference runs one padded batch; we tile by engine capacity
             # Philox streams are keyed (seed; row, frame, group) with the row index local to a tile: give every
             # tile its own key so row b of two tiles never shares uniforms
             sp_t = sp if s == 0 else dataclasses.replace(sp, seed=(sp.seed ^ (s * 0x9E3779B97F4A7C15)) & (2 ** 63 - 1))
-            out += self.engine.generate(embeds[s:s + mb], tr[s:s + mb], pad, sp_t)
-        return out, [None] * len(out)
+            c, h = self.engine.generate(embeds[s:s + mb], tr[s:s + mb], pad, sp_t, return_hidden=True)
+            out += c
+            hids += h
+        return out, hids
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -293,3 +293,27 @@ def test_long_context_cross_cta_split_attention():
         for f in range(N + 1):
             _check_logits(tl[f], ref.record["talker_logits"][f], f"ctx{lens} talker frame {f}")
         eng.close()
+
+
+def test_per_step_hidden_states_second_return_value():
+    """generate()'s second return (modeling_qwen3_tts.py:2281,2290): the final-norm hidden state of the newest position
+    of every step.  Check: codec_head(hidden[s]) reproduces the step's own raw logits, for every row and step."""
+    cfg = _tiny()
+    Wb, _ = Hh.bf16_weights(OT.random_weights(cfg, seed=12))
+    lens = [7, 12, 5]
+    B, N = len(lens), 6
+    embs, trail, pad = Hh.make_inputs(cfg, lens, [2, 0, 1], seed=14)
+    sp = OT.SamplingCfg(do_sample=True, subtalker_dosample=True, max_new_tokens=N + 1, suppress_eos=True, seed=3)
+    eng = _engine(cfg, Wb)
+    V = cfg.talker.vocab_size
+    tl = torch.zeros(N + 1, B, V, dtype=torch.float32, device=DEV)
+    eng.set_debug(None, 0, tl, None)
+    codes, hid = eng.generate(embs, trail, pad, Hh.to_pkg_sampling(sp), return_hidden=True)
+    eng.set_debug(None, 0, None, None)
+    head = Wb["talker.codec_head.weight"].float().to(DEV)
+    for b in range(B):
+        assert hid[b].shape == (codes[b].shape[0], cfg.talker.hidden_size) and codes[b].shape[0] == N
+        lg = hid[b].float() @ head.t()                                     # (N, V): steps 0..N-1
+        ref = tl[:N, b]
+        assert (lg - ref).abs().max().item() < 0.05, (b, (lg - ref).abs().max().item())
+    eng.close()

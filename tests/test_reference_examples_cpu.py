@@ -17,9 +17,10 @@ def stubbed(monkeypatch):
         def __init__(self, cfg, w, device=None, max_batch=None, max_ctx=None):
             self.max_batch, self.G = max_batch, cfg.num_code_groups
 
-        def generate(self, embeds, trail, pad, sp):
+        def generate(self, embeds, trail, pad, sp, return_hidden=False):
             assert all(e.dim() == 2 for e in embeds) and len(embeds) == len(trail)
-            return [torch.full((3 + i, self.G), i, dtype=torch.long) for i in range(len(embeds))]
+            codes = [torch.full((3 + i, self.G), i, dtype=torch.long) for i in range(len(embeds))]
+            return (codes, [torch.zeros(c.shape[0], 8) for c in codes]) if return_hidden else codes
 
     class _Dec:
         total_upsample = 1920
