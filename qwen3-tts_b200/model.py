@@ -114,11 +114,154 @@ class Qwen3TTSForConditionalGenerationB200:
         text_embed = torch.cat([text_embed] + [tts_pad_embed] * (codec_lens - text_lens), dim=1)
         return text_embed + codec_embed, tts_pad_embed
 
+    # ------------------------------------------------------------------ batched prefill assembly
+    def _plan_sample(self, input_id, instruct, ref_id, vcp, index, language, speaker, non_streaming_mode):
+        """Index plan of one sample (:2086-2234): every prefill / trailing position is `TP(text id) + codec source`
+        with either side optional.  Returns (text_ids, codec_src, trailing_ids); text id -1 = no text part; codec_src
+        entries: None | ("ce", id) | ("spk",) | ("icl", frame)."""
+        cfg = self.cfg
+        ids = [int(x) for x in input_id.reshape(-1).tolist()]
+        BOS, EOS, PAD = cfg.tts_bos_token_id, cfg.tts_eos_token_id, cfg.tts_pad_token_id
+        has_spk_vec = False
+        speaker_id = None
+        if vcp is None:
+            if not (speaker == "" or speaker is None):
+                if speaker.lower() not in self.spk_id:
+                    raise NotImplementedError(f"Speaker {speaker} not implemented")
+                speaker_id = self.spk_id[speaker.lower()]
+        else:
+            has_spk_vec = bool(vcp["x_vector_only_mode"][index] or vcp["icl_mode"][index])
+        assert language is not None
+        if language.lower() == "auto":
+            language_id = None
+        else:
+            if language.lower() not in self.codec_language_id:
+                raise NotImplementedError(f"Language {language} not implemented")
+            language_id = self.codec_language_id[language.lower()]
+        if (language.lower() in ["chinese", "auto"] and speaker != "" and speaker is not None
+                and self.spk_is_dialect.get(speaker.lower(), False) is not False):
+            language_id = self.codec_language_id[self.spk_is_dialect[speaker.lower()]]
+        if language_id is None:
+            cids = [cfg.codec_nothink_id, cfg.codec_think_bos_id, cfg.codec_think_eos_id]
+        else:
+            cids = [cfg.codec_think_id, cfg.codec_think_bos_id, language_id, cfg.codec_think_eos_id]
+        C = [("ce", c) for c in cids]
+        if has_spk_vec:
+            C.append(("spk",))
+        elif speaker_id is not None:
+            C.append(("ce", speaker_id))
+        C += [("ce", cfg.codec_pad_id), ("ce", cfg.codec_bos_id)]
+        text, codec = [], []
+        if instruct is not None:
+            for t in instruct.reshape(-1).tolist():
+                text.append(int(t)); codec.append(None)
+        for t in ids[:3]:                                    # role tokens (:2177-2179)
+            text.append(t); codec.append(None)
+        n_over = len(C) - 1                                  # overlay (:2182-2184)
+        text += [PAD] * (n_over - 1) + [BOS]
+        codec += C[:-1]
+        icl = vcp is not None and vcp["ref_code"] is not None and vcp["icl_mode"][index]
+        if icl:                                              # generate_icl_prompt (:1968-2019)
+            rid = [int(x) for x in ref_id.reshape(-1).tolist()][3:-2]
+            tstream = rid + ids[3:-5] + [EOS]
+            n_ref = int(vcp["ref_code"][index].shape[0])
+            cstream = [("ce", cfg.codec_bos_id)] + [("icl", t) for t in range(n_ref)]
+            Lt, Lc = len(tstream), len(cstream)
+            if non_streaming_mode:
+                text += tstream + [PAD] * Lc
+                codec += [("ce", cfg.codec_pad_id)] * Lt + cstream
+                trailing = [PAD]
+            elif Lt > Lc:
+                text += tstream[:Lc]; codec += cstream
+                trailing = tstream[Lc:]
+            else:
+                text += tstream + [PAD] * (Lc - Lt); codec += cstream
+                trailing = [PAD]
+        elif non_streaming_mode:                             # (:2203-2227)
+            body = ids[3:-5]
+            text += body + [EOS] + [PAD]
+            codec += [("ce", cfg.codec_pad_id)] * (len(body) + 1) + [("ce", cfg.codec_bos_id)]
+            trailing = [PAD]
+        else:                                                # (:2199-2202, :2229-2232)
+            text.append(ids[3]); codec.append(C[-1])
+            trailing = ids[4:-5] + [EOS]
+        return text, codec, trailing
+
     @torch.no_grad()
     def build_prefill(self, input_ids, instruct_ids=None, ref_ids=None, voice_clone_prompt=None, languages=None,
                       speakers=None, non_streaming_mode=False):
-        """:2068-2237 — per-sample (unpadded) prefill embeddings + trailing text + tts_pad.  The reference's left
+        """:2068-2237 — per-sample (unpadded) prefill embeddings + trailing text + tts_pad, computed for the WHOLE request
+        list with a fixed number of batched device launches (one text-embedding gather + one ResizeMLP over every text
+        token of every sample, one codec-embedding gather, one 16-codebook gather-and-sum over all ICL reference
+        frames, one add) instead of dozens of small launches per sample.  The index plan is host-side integer work;
+        `build_prefill_per_sample` is the statement-by-statement restatement it must equal.  The reference's left
         padding / attention mask (:2239-2254) is not materialised: the engine takes per-sequence lengths."""
+        cfg, dev = self.cfg, self.device
+        n = len(input_ids)
+        if speakers is None:
+            speakers = [None] * n
+        plans = []
+        for i in range(n):
+            ins = instruct_ids[i] if instruct_ids is not None else None
+            rid = ref_ids[i] if ref_ids is not None else None
+            plans.append(self._plan_sample(input_ids[i], ins, rid, voice_clone_prompt, i, languages[i], speakers[i], non_streaming_mode))
+        H = self.codec_embedding.shape[1]
+        # ---- text side: every text id of every sample (prefill + trailing) + the three specials, ONE ResizeMLP
+        flat_text, seg = [], []
+        for text, _, trailing in plans:
+            seg.append((len(flat_text), len(text), len(trailing)))
+            flat_text += [t if t >= 0 else cfg.tts_pad_token_id for t in text] + trailing
+        flat_text += [cfg.tts_bos_token_id, cfg.tts_eos_token_id, cfg.tts_pad_token_id]
+        tp = self._tp(torch.tensor(flat_text, dtype=torch.long, device=dev)[None])[0]          # (Ntext, H)
+        tts_pad_embed = tp[-1]
+        # ---- codec side: gather ids, speaker vectors, ICL frame sums
+        ce_ids, ce_pos, spk_pos, icl_pos, icl_rows = [], [], [], [], []
+        total = 0
+        offs = []
+        for i, (text, codec, _) in enumerate(plans):
+            offs.append(total)
+            for p, c in enumerate(codec):
+                if c is None:
+                    continue
+                if c[0] == "ce":
+                    ce_ids.append(c[1]); ce_pos.append(total + p)
+                elif c[0] == "spk":
+                    spk_pos.append((total + p, i))
+                else:
+                    icl_pos.append(total + p); icl_rows.append((i, c[1]))
+            total += len(text)
+        cpart = torch.zeros(total, H, dtype=self.dtype, device=dev)
+        if ce_ids:
+            cpart[torch.tensor(ce_pos, device=dev)] = F.embedding(torch.tensor(ce_ids, dtype=torch.long, device=dev), self.codec_embedding)
+        for pos, i in spk_pos:
+            cpart[pos] = voice_clone_prompt["ref_spk_embedding"][i].to(dev).to(self.dtype).reshape(-1)
+        if icl_rows:
+            G = cfg.num_code_groups
+            ref = torch.stack([voice_clone_prompt["ref_code"][i][t].to(dev) for i, t in icl_rows])       # (R, G)
+            parts = [F.embedding(ref[:, :1], self.codec_embedding)]
+            for g in range(1, G):
+                parts.append(F.embedding(ref[:, g:g + 1], self.cp_embeddings[g - 1]))
+            cpart[torch.tensor(icl_pos, device=dev)] = torch.cat(parts, dim=1).sum(1)                    # == :1983-1998
+        # ---- assemble: position = text part + codec part (either may be absent)
+        embeds, trailing = [], []
+        for i, (text, codec, trail) in enumerate(plans):
+            t0, nt, ntr = seg[i]
+            tpart = tp[t0:t0 + nt]
+            has_text = torch.tensor([t >= 0 for t in text], device=dev)
+            has_codec = torch.tensor([c is not None for c in codec], device=dev)
+            cp_i = cpart[offs[i]:offs[i] + nt]
+            both = tpart + cp_i
+            emb = torch.where((has_text & has_codec)[:, None], both, torch.where(has_text[:, None], tpart, cp_i))
+            embeds.append(emb)
+            trailing.append(tp[t0 + nt:t0 + nt + ntr])
+        return embeds, trailing, tts_pad_embed.reshape(-1)
+
+    @torch.no_grad()
+    def build_prefill_per_sample(self, input_ids, instruct_ids=None, ref_ids=None, voice_clone_prompt=None, languages=None,
+                      speakers=None, non_streaming_mode=False):
+        """:2068-2237 restated statement by statement (one small embedding / MLP launch per piece and per sample, as
+        the reference does).  Kept as the readable specification of `build_prefill`, which computes the same tensors
+        with a handful of batched launches; tests/test_wrappers_cpu.py requires the two to agree exactly."""
         cfg = self.cfg
         n = len(input_ids)
         pieces: List[List[torch.Tensor]] = [[] for _ in range(n)]

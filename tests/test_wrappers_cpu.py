@@ -214,3 +214,43 @@ def test_stream_synthesize_batches_rows_like_per_row_decoding():
             assert np.concatenate(parts[b]).shape[0] == f.shape[0] * up
     # packet 0: all three rows in one call; packet 1: rows 0 and 2 (4 new frames) + row 1 (3 new frames) = 2 calls; packet 2: 1 call
     assert [c[0] for c in calls[:4 + 0] if True][:1] == [3]
+
+
+def test_batched_prefill_assembly_equals_per_sample_restatement():
+    """build_prefill (batched gathers / one ResizeMLP for every text token of every sample) must equal the
+    statement-by-statement restatement of modeling_qwen3_tts.py:2068-2237 exactly, in bf16, for every mode mix:
+    instruct / no instruct, known language / auto / dialect override, speaker id / x-vector / ICL, streaming and not."""
+    from oracle import talker as OT
+    from tests import helpers as Hh
+    from qwen3_tts_b200.model import Qwen3TTSForConditionalGenerationB200 as M
+    cfg = OT.cfg_tiny()
+    W = OT.random_weights(cfg, seed=4, with_text=True, text_vocab=1000)
+    spk_id = {"alice": 3000, "bob": 3001}
+    lang = {"english": 2050, "chinese": 2055, "sichuan_dialect": 2060}
+    dial = {"alice": False, "bob": "sichuan_dialect"}
+    m = M.__new__(M)
+    M.__init__(m, Hh.to_pkg_cfg(cfg), {k: v.to(torch.bfloat16) for k, v in W.items()}, device="cpu", spk_id=spk_id, spk_is_dialect=dial,
+               codec_language_id=lang, engine=object())
+    g = torch.Generator().manual_seed(1)
+    ids = lambda n: torch.randint(0, 990, (1, n), generator=g)  # noqa: E731
+    H = cfg.talker.hidden_size
+
+    def same(a, b):
+        ea, ta, pa = a
+        eb, tb, pb = b
+        assert len(ea) == len(eb)
+        for x, y in zip(ea + ta + [pa], eb + tb + [pb]):
+            assert x.shape == y.shape and torch.equal(x, y), (x.shape, y.shape, (x.float() - y.float()).abs().max())
+
+    for nsm in (False, True):
+        # custom voice / voice design: instruct on some rows, dialect override, auto language, no speaker
+        kw = dict(input_ids=[ids(14), ids(10), ids(21)], instruct_ids=[ids(6), None, ids(9)], languages=["English", "auto", "Chinese"],
+                  speakers=["alice", "bob", None], non_streaming_mode=nsm)
+        same(m.build_prefill(**kw), m.build_prefill_per_sample(**kw))
+        # voice clone: ICL (text longer and shorter than the reference codes) and x-vector-only rows
+        vcp = dict(ref_spk_embedding=[torch.randn(H, generator=g), torch.randn(H, generator=g), torch.randn(H, generator=g)],
+                   x_vector_only_mode=[False, True, False], icl_mode=[True, False, True],
+                   ref_code=[torch.randint(0, 2000, (5, 16), generator=g), None, torch.randint(0, 2000, (30, 16), generator=g)])
+        kw = dict(input_ids=[ids(25), ids(12), ids(13)], ref_ids=[ids(11), None, ids(9)], voice_clone_prompt=vcp,
+                  languages=["English", "auto", "English"], non_streaming_mode=nsm)
+        same(m.build_prefill(**kw), m.build_prefill_per_sample(**kw))
