@@ -93,10 +93,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) q3_step_kernel(const __grid_co
     reinterpret_cast<uint4*>(smem + P.plan.nw_off)[tid] = reinterpret_cast<const uint4*>(s_ph[0].norm_w)[tid];
   if (s_ph[0].type == PH_ATTN) attn_prefetch(s_ph[0], P, smem + P.plan.x_off, st->step);  // (synthetic profiling programs only)
 
-  // L2 eviction priority of the weight stream: everything is read once per frame-step or is too large to stay
-  // (an evict_last fraction for the code predictor's layers made no measurable difference: profiles/r02_l2_policy_ab.txt)
-  uint64_t policy;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+  // L2 eviction priorities of the weight stream (createpolicy): the talker and the 15 heads are read once per
+  // frame-step -> evict_first; the code predictor's layer weights (157 MB) are re-read on each of its 15 passes -> a
+  // fixed, address-hashed fraction of their lines is evict_last, i.e. stays in the 126 MB L2 between passes and is not
+  // re-fetched from HBM.  No effect on time (the kernel is latency-bound); the effect is on DRAM traffic
+  // (profiles/r02_l2_residency.txt).
+  uint64_t pol_stream, pol_keep;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol_keep) : "f"(P.keep_fraction));
 
   // ---- this warp's weight ring: start streaming before anything else happens
   Ring rg;
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) q3_step_kernel(const __grid_co
     ring_init(rg, P.runs + o0, (int)(o1 - o0), (long long)(o1 - o0) * niter);
   }
 #pragma unroll 1
-  for (int i = 0; i < R; ++i) ring_issue(rg, P, lane, policy);
+  for (int i = 0; i < R; ++i) ring_issue(rg, P, lane, pol_stream, pol_keep);
   __syncthreads();
 
   const int step_base = st->step;
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) q3_step_kernel(const __grid_co
         PROF_MARK(6);
       }
       const int type = ph.type;
-      if (type == PH_GEMV) xpar = gemv_phase<NT>(ph, meta[pi], P, rg, smem, &s_tab, xbar, xpar, policy, frame);
+      if (type == PH_GEMV) xpar = gemv_phase<NT>(ph, meta[pi], P, rg, smem, &s_tab, xbar, xpar, pol_stream, pol_keep, frame);
       else if (type == PH_ATTN) attn_phase(ph, P, smem + P.plan.x_off, frame);
       else sample_phase(ph, P, smem + P.plan.x_off, frame, P.mode == 0);
       if (dhave) reinterpret_cast<uint32_t*>(&s_ph[slot ^ 1])[tid] = dreg;
@@ -444,7 +448,7 @@ static int add_layers(q3_engine* e, std::vector<Phase>& prog, const char* pfx, S
 // Run table of a program: for every (CTA, warp) the sequence of contiguous weight runs (offset from the weight arena
 // base in 16-byte units, number of 1 KB blocks) of ONE pass over the program, enumerated with the same iterator the
 // model check in tests/test_ring_model.py exercises.  The kernel's consumer loop derives the same runs from run_geom().
-static int build_piece_table(q3_engine* e, const std::vector<Phase>& prog, int SB, PieceTable* out) {
+static int build_piece_table(q3_engine* e, const std::vector<Phase>& prog, int SB, PieceTable* out, int keep_phases = 0) {
   const int grid = e->sm_count, n = (int)prog.size();
   (void)SB;
   std::vector<uint2> pieces;
@@ -471,7 +475,11 @@ static int build_piece_table(q3_engine* e, const std::vector<Phase>& prog, int S
       q3ring::prod_init(it);
       q3ring::prod_next_run(it, meta.data(), n, 1, warp);
       while (!it.done) {
-        pieces.push_back(make_uint2((uint32_t)(q3ring::prod_piece_offset(it) >> 4), (uint32_t)(it.u1 - it.u)));
+        // bit 31 of the length: the run belongs to weights that are re-read within a frame-step (the code predictor's
+        // LAYERS: phases before keep_phases that are not an LM head / projection) -> L2 evict_last fraction
+        const Phase& ph = prog[it.pi];
+        const bool keep = it.pi < keep_phases && ph.epi != EPI_LOGITS && ph.epi != EPI_BIAS;
+        pieces.push_back(make_uint2((uint32_t)(q3ring::prod_piece_offset(it) >> 4), (uint32_t)(it.u1 - it.u) | (keep ? 0x80000000u : 0u)));
         q3ring::prod_next_run(it, meta.data(), n, 1, warp);
       }
     }
@@ -614,7 +622,7 @@ static int build_programs(q3_engine* e, int B) {
     return 1;
   Q3_REQUIRE((int)F.size() <= MAX_PHASES, "frame program has %d phases (max %d)", (int)F.size(), MAX_PHASES);
   if (build_piece_table(e, e->prog_head, e->plan_head.slot_blocks, &e->pt_head) ||
-      build_piece_table(e, e->prog_frame, e->plan_frame.slot_blocks, &e->pt_frame))
+      build_piece_table(e, e->prog_frame, e->plan_frame.slot_blocks, &e->pt_frame, e->cp_phases))
     return 1;
   // upload (a batch-size change is rare: wait for launches that may still walk the old program)
   Q3_CUDA(cudaDeviceSynchronize());
@@ -711,7 +719,7 @@ extern "C" int q3_engine_finalize(q3_engine* e) {
   e->w_cp_stream_bytes = 2.0 * ((c.num_code_groups - 1) * (cpl + proj) + heads);
   // L2 residency of the code predictor's layer weights (re-read on each of its passes): keep ~80 MB of them at
   // evict_last priority beside the talker's evict_first stream (126 MB L2)
-  if (!getenv("Q3_KEEP_FRACTION")) e->keep_fraction = (float)std::min(1.0, 80e6 / (2.0 * cpl));
+  if (!getenv("Q3_KEEP_FRACTION")) e->keep_fraction = (float)std::min(1.0, 96e6 / (2.0 * cpl));
   e->finalized = true;
   return 0;
 }

@@ -161,21 +161,22 @@ struct Ring {
   long long runs_left;     // runs of this launch not yet started (including the one in `nxt`)
   uint32_t cur_off;        // current run: next block's offset / 16
   int cur_left;            // blocks of the current run not yet requested
+  bool cur_keep;           // current run belongs to weights that are re-read within a frame (code-predictor layers)
   uint2 nxt;               // the following run (prefetched a whole run ahead: its L2 latency is never exposed)
   int outstanding;         // pieces requested, not yet consumed
 };
 
 __device__ __forceinline__ void ring_init(Ring& rg, const uint2* list, int len, long long total_runs) {
   rg.list = list; rg.len = len; rg.ri = 0; rg.runs_left = total_runs;
-  rg.cur_off = 0; rg.cur_left = 0;
+  rg.cur_off = 0; rg.cur_left = 0; rg.cur_keep = false;
   rg.nxt = len > 0 ? __ldg(list) : make_uint2(0, 0);
 }
 
 // request the next piece (<= SB blocks of the current run) into slot p_slot; lane 0 issues, every lane keeps the books
-__device__ __forceinline__ void ring_issue(Ring& rg, const KParams& P, int lane, uint64_t policy) {
+__device__ __forceinline__ void ring_issue(Ring& rg, const KParams& P, int lane, uint64_t pol_stream, uint64_t pol_keep) {
   if (rg.cur_left == 0) {
     if (rg.runs_left <= 0) return;
-    rg.cur_off = rg.nxt.x; rg.cur_left = (int)rg.nxt.y;
+    rg.cur_off = rg.nxt.x; rg.cur_left = (int)(rg.nxt.y & 0x7fffffffu); rg.cur_keep = (rg.nxt.y >> 31) != 0;
     --rg.runs_left;
     if (++rg.ri == rg.len) rg.ri = 0;
     rg.nxt = __ldg(rg.list + rg.ri);
@@ -186,8 +187,12 @@ __device__ __forceinline__ void ring_issue(Ring& rg, const KParams& P, int lane,
     const uint32_t bar = rg.full + 8u * rg.p_slot;
     mbar_expect_tx(bar, bytes);
     const char* src = P.wbase + ((size_t)rg.cur_off << 4);
+    // L2 priority of the line fill: pol_stream = evict_first (read once per frame-step), pol_keep = a fixed,
+    // address-hashed fraction evict_last (the code predictor's layer weights are re-read on each of its 15 passes:
+    // what stays in L2 is not re-fetched from HBM; measured traffic: profiles/r02_l2_residency.txt)
+    const uint64_t pol = rg.cur_keep ? pol_keep : pol_stream;
     if (P.flags & 4) bulk_g2s_plain(rg.slots + (uint32_t)(rg.p_slot * rg.SB) * 1024u, src, bytes, bar);
-    else bulk_g2s(rg.slots + (uint32_t)(rg.p_slot * rg.SB) * 1024u, src, bytes, bar, policy);
+    else bulk_g2s(rg.slots + (uint32_t)(rg.p_slot * rg.SB) * 1024u, src, bytes, bar, pol);
   }
   rg.cur_off += (uint32_t)nb << 6;
   rg.cur_left -= nb;
@@ -195,11 +200,11 @@ __device__ __forceinline__ void ring_issue(Ring& rg, const KParams& P, int lane,
   ++rg.outstanding;
 }
 
-__device__ __forceinline__ void ring_release(Ring& rg, const KParams& P, int lane, uint64_t policy) {
+__device__ __forceinline__ void ring_release(Ring& rg, const KParams& P, int lane, uint64_t pol_stream, uint64_t pol_keep) {
   __syncwarp();  // every lane's reads of the slot are done before the async proxy overwrites it
   if (++rg.c_slot == rg.R) { rg.c_slot = 0; rg.c_par ^= 1; }
   --rg.outstanding;
-  ring_issue(rg, P, lane, policy);
+  ring_issue(rg, P, lane, pol_stream, pol_keep);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -366,7 +371,7 @@ __device__ __forceinline__ void flush_acc(float (&acc)[NACC][NT][4], float* pp, 
 // The phase body.  `m` is this CTA's meta of the phase (tiles owned, K blocks); the weights arrive through the ring.
 template <int NT>
 __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, const KParams& P, Ring& rg, unsigned char* smem,
-                                               RoundTab* tab, uint32_t xbar, uint32_t xpar, uint64_t policy, int frame) {
+                                               RoundTab* tab, uint32_t xbar, uint32_t xpar, uint64_t pol_stream, uint64_t pol_keep, int frame) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int KB = m.kb, K = KB * 32, epi = ph.epi, ntc = m.ntc;
@@ -526,7 +531,7 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
           kbi = 0;
           ++seg;
         }
-        ring_release(rg, P, lane, policy);
+        ring_release(rg, P, lane, pol_stream, pol_keep);
         if (!staged) {
 #pragma unroll
           for (int i = 0; i < PB; ++i)

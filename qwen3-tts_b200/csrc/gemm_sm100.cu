@@ -1,9 +1,13 @@
-// tcgen05 tap-GEMM kernel (see gemm_sm100.cuh).  Warp-specialised, one 128 x bn output tile per CTA:
-//   warp 0  : TMA producer (A tile via a 3-D map with a per-tap row shift, W tile via a 2-D map), 4-stage ring
-//   warp 1  : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=bn, K=16, bf16 -> fp32 in TMEM)
-//   warps 2-5: epilogue — tcgen05.ld the accumulator (one output row per thread), fused bias / LayerScale /
-//              residual / SnakeBeta / GELU / SwiGLU, bf16 stores.
+// tcgen05 tap-GEMM kernel (see gemm_sm100.cuh).  Warp-specialised and PERSISTENT: a CTA walks 128 x bn output tiles
+// (tile = blockIdx.x, += gridDim.x) with TWO accumulators in TMEM, so the epilogue of tile i (tcgen05.ld, bias /
+// LayerScale / residual / SnakeBeta / GELU / SwiGLU, bf16 stores) overlaps the TMA + MMA mainloop of tile i+1:
+//   warp 0  : TMA producer (A tile via a 3-D map with a per-tap row shift, W tile via a 2-D map), 4-stage ring that
+//             keeps running across tiles
+//   warp 1  : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=bn, K=16, bf16 -> fp32 in TMEM); waits for
+//             the accumulator it is about to overwrite (tmem_empty), commits tmem_full when a tile is complete
+//   warps 2-5: epilogue — one output row per thread; arrive on tmem_empty when the accumulator has been read.
 #include "gemm_sm100.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -14,7 +18,7 @@ constexpr int A_BYTES = BM * BK * 2;        // 16 KB
 constexpr int B_BYTES_MAX = 256 * BK * 2;   // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
 constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers: full[S], empty[S], tmem_full[2], tmem_empty[2], tmem slot*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -85,26 +89,28 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + er
 __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_constant__ GemmPlan p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // full[S], empty[S], tmem_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // full[S], empty[S], tmem_full[2], tmem_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * p.bn, b = blockIdx.z;
   const int kpb = p.Kp / BK;
   const int nkb = p.ntaps * kpb;
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
+  const int mtiles = (p.T + BM - 1) / BM, ntiles = (p.N + p.bn - 1) / p.bn;
+  const int total = mtiles * ntiles * p.B;
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull0 = smem_u32(bars + 2 * STAGES),
+                 tempty0 = smem_u32(bars + 2 * STAGES + 2);
   const uint32_t b_bytes = (uint32_t)p.bn * BK * 2;
-  uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)p.bn) tmem_cols <<= 1;
+  uint32_t acc_cols = 32;  // columns of one accumulator (power of two >= bn); two accumulators are allocated
+  while (acc_cols < (uint32_t)p.bn) acc_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmW) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    mbar_init(tfull, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * acc_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -114,41 +120,61 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        if (kb >= STAGES) mbar_wait(empty0 + 8 * s, ((kb / STAGES) - 1) & 1);
-        const int tap = kb / kpb, k0 = (kb - tap * kpb) * BK;
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
-        mbar_expect_tx(full0 + 8 * s, A_BYTES + b_bytes);
-        tma_load_3d(sa, &p.tmA, k0, m0 + p.shift[tap] + p.a_row0, b, full0 + 8 * s);
-        tma_load_2d(sb, &p.tmW, tap * p.Kp + k0, n0, full0 + 8 * s);
+      int it = 0;  // k-blocks issued so far, over all tiles: ring position
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int nt = tile % ntiles, mt = (tile / ntiles) % mtiles, b = tile / (ntiles * mtiles);
+        const int m0 = mt * BM, n0 = nt * p.bn;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          if (it >= STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
+          const int tap = kb / kpb, k0 = (kb - tap * kpb) * BK;
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+          mbar_expect_tx(full0 + 8 * s, A_BYTES + b_bytes);
+          tma_load_3d(sa, &p.tmA, k0, m0 + p.shift[tap] + p.a_row0, b, full0 + 8 * s);
+          tma_load_2d(sb, &p.tmW, tap * p.Kp + k0, n0, full0 + 8 * s);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=bn, M=128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(full0 + 8 * s, (kb / STAGES) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
-        const uint64_t ad = make_sdesc(sa), bd = make_sdesc(sb);
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) start-address field
-          umma_bf16(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+      int it = 0, lt = 0;  // ring position; local tile counter (accumulator = lt & 1)
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        if (lt >= 2) {  // the epilogue must have drained this accumulator (tile lt-2)
+          mbar_wait(tempty0 + 8 * acc, ((lt >> 1) - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        umma_commit(empty0 + 8 * s);          // frees the smem slot once these MMAs have read it
-        if (kb == nkb - 1) umma_commit(tfull);  // accumulator complete
+        const uint32_t tacc = tmem_base + (uint32_t)acc * acc_cols;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
+          const uint64_t ad = make_sdesc(sa), bd = make_sdesc(sb);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (>>4) start-address field
+            umma_bf16(tacc, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+          umma_commit(empty0 + 8 * s);                     // frees the smem slot once these MMAs have read it
+          if (kb == nkb - 1) umma_commit(tfull0 + 8 * acc);  // accumulator complete
+        }
       }
     }
   } else {
     // ---- epilogue: warp (w % 4) owns TMEM lanes [32*(w%4), +32); thread = one output row
     const int q = warp & 3;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+    const int acc = lt & 1;
+    const int nt = tile % ntiles, mt = (tile / ntiles) % mtiles, b = tile / (ntiles * mtiles);
+    const int m0 = mt * BM, n0 = nt * p.bn;
     const int m = m0 + q * 32 + lane;
-    mbar_wait(tfull, 0);
+    mbar_wait(tfull0 + 8 * acc, (lt >> 1) & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tacc = tmem_base + (uint32_t)acc * acc_cols;
     const GemmEpilogue& E = p.ep;
     const bool row_ok = m < p.T;
     const size_t mrow = (size_t)(row_ok ? m : 0) * (size_t)p.N;
@@ -156,7 +182,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
                  res_off = (size_t)b * (size_t)p.resid_bs + mrow;
     for (int c0 = 0; c0 < p.bn; c0 += 16) {
       uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld16(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       const int n = n0 + c0;
       if (!row_ok || n >= p.N) continue;
@@ -234,12 +260,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
         }
       }
     }
+    // this warp has read its 32 lanes of the accumulator: hand it back to the MMA issuer (4 arrivals = 4 warps)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * acc) : "memory");
+    }  // tile loop
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * acc_cols) : "memory");
   }
 }
 
@@ -247,6 +278,7 @@ typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeFn g_encode = nullptr;
+int g_sm_count = 0;
 
 }  // namespace
 
@@ -259,6 +291,11 @@ int gemm_init() {
     g_encode = reinterpret_cast<EncodeFn>(fn);
   }
   Q3_CUDA(cudaFuncSetAttribute(tap_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  if (g_sm_count == 0) {
+    int dev = 0;
+    Q3_CUDA(cudaGetDevice(&dev));
+    Q3_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
   return 0;
 }
 
@@ -322,7 +359,8 @@ int gemm_pick_bn(int N, int mtiles, int B) {
 }
 
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
-  dim3 grid((plan.T + BM - 1) / BM, (plan.N + plan.bn - 1) / plan.bn, plan.B);
+  const long long total = (long long)((plan.T + BM - 1) / BM) * ((plan.N + plan.bn - 1) / plan.bn) * plan.B;
+  const int grid = (int)std::min<long long>(total, g_sm_count > 0 ? g_sm_count : 148);  // persistent: one CTA per SM walks the tiles
   tap_gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(plan);
   Q3_CUDA(cudaGetLastError());
   return 0;
