@@ -719,7 +719,7 @@ extern "C" int q3_engine_finalize(q3_engine* e) {
   e->w_cp_stream_bytes = 2.0 * ((c.num_code_groups - 1) * (cpl + proj) + heads);
   // L2 residency of the code predictor's layer weights (re-read on each of its passes): keep ~80 MB of them at
   // evict_last priority beside the talker's evict_first stream (126 MB L2)
-  if (!getenv("Q3_KEEP_FRACTION")) e->keep_fraction = (float)std::min(1.0, 96e6 / (2.0 * cpl));
+  if (!getenv("Q3_KEEP_FRACTION")) e->keep_fraction = (float)std::min(1.0, 68e6 / (2.0 * cpl));  // measured: more than ~75 MB of evict_last lines thrash (profiles/r02_l2_residency.txt)
   e->finalized = true;
   return 0;
 }
