@@ -5,7 +5,7 @@
 //             keeps running across tiles
 //   warp 1  : TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=bn, K=16, bf16 -> fp32 in TMEM); waits for
 //             the accumulator it is about to overwrite (tmem_empty), commits tmem_full when a tile is complete
-//   warps 2-9: epilogue — one output row per thread, two warps per TMEM lane quadrant (alternating 16-column chunks);
+//   warps 2-17: epilogue — one output row per thread, four warps per TMEM lane quadrant (interleaved 16-column chunks);
 //             arrive on tmem_empty when the accumulator has been read.
 #include "gemm_sm100.cuh"
 #include <algorithm>
@@ -18,7 +18,10 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;        // 16 KB
 constexpr int B_BYTES_MAX = 256 * BK * 2;   // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
-constexpr int GEMM_THREADS = 320;  // producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant)
+constexpr int EPI_WARPS = 16;                        // four per TMEM lane quadrant: the epilogue (tcgen05.ld + SnakeBeta / GELU /
+                                                     // residual + stores) is what bounds the short-K convolutions (measured: 4 warps
+                                                     // 28.5 ms, 8 warps 18.3 ms for the 8 x 125-frame codec)
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;    // producer warp, MMA warp, epilogue warps
 constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers: full[S], empty[S], tmem_full[2], tmem_empty[2], tmem slot*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmW) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
     // ---- epilogue: warp (w % 4) owns TMEM lanes [32*(w%4), +32); thread = one output row; the two warps of a
     // quadrant split the tile's columns (16-column chunks alternate) so the epilogue keeps up with short mainloops
     const int q = warp & 3;
-    const int chalf = (warp - 2) >> 2;  // 0 or 1
+    const int chalf = (warp - 2) >> 2;  // which 16-column chunk (mod EPI_WARPS/4) this warp takes
     int lt = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
     const int acc = lt & 1;
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
     const size_t mrow = (size_t)(row_ok ? m : 0) * (size_t)p.N;
     const size_t raw_off = (size_t)b * (size_t)p.raw_bs + mrow, act_off = (size_t)b * (size_t)p.act_bs + mrow,
                  res_off = (size_t)b * (size_t)p.resid_bs + mrow;
-    for (int c0 = chalf * 16; c0 < p.bn; c0 += 32) {
+    for (int c0 = chalf * 16; c0 < p.bn; c0 += 16 * (EPI_WARPS / 4)) {
       uint32_t v[16];
       tmem_ld16(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
         }
       }
     }
-    // this warp has read its 32 lanes of the accumulator: hand it back to the MMA issuer (8 arrivals = 8 warps)
+    // this warp has read its 32 lanes of the accumulator: hand it back to the MMA issuer (one arrival per epilogue warp)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncwarp();
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * acc) : "memory");
