@@ -342,6 +342,77 @@ def decode_probe(eng, q, cfg, args, spk, B, N, dev, greedy=False):
             "ms_per_frame_step": dec / N, "first_packet_ms": fp, "roofline_frac_decode": a_bytes / (dec / N / 1000.0) / 1e9 / hbm_peak()[0]}
 
 
+REF_FRAMES = 38   # 3 s of prompt audio at 12.5 Hz (72000 samples / 1920, rounded up)
+
+
+def voice_clone_probe(eng, q, cfg, W, args, spk, B, N, dev):
+    """BASELINE config[4] composed at full 1.7B-Base shape, host in / host out: 3 s of prompt audio per row ->
+    codec encoder (ref codes) + speaker x-vector -> ICL prefill (role prefix, x-vector row, BOS + 38 reference frames whose
+    embedding is the sum of the 16 codebook embeddings, text rows as trailing input) -> N frame-steps -> codec decode of the
+    38 + N frames -> proportional cut of the reference part (inference/qwen3_tts_model.py:566-598).  Random weights:
+    a timing of the composed path, stage by stage; parity of each stage is in tests/ (test_gpu_voice_clone.py et al.)."""
+    from qwen3_tts_b200 import synthetic
+    from qwen3_tts_b200.codec_encoder import CodecEncoder
+    from qwen3_tts_b200.config import EncoderConfig, SpeakerEncoderConfig
+    from qwen3_tts_b200.speaker_encoder import SpeakerEncoder
+    H, G = cfg.talker.hidden_size, cfg.num_code_groups
+    ecfg, scfg = EncoderConfig(), SpeakerEncoderConfig(enc_dim=H)
+    cenc = CodecEncoder(ecfg, synthetic.random_encoder_weights(ecfg, seed=2), device=dev)
+    senc = SpeakerEncoder(scfg, synthetic.random_speaker_encoder_weights(scfg, seed=1), device=dev)
+    tabs = [W["talker.model.codec_embedding.weight"]] + [W[f"talker.code_predictor.model.codec_embedding.{j}.weight"] for j in range(G - 1)]
+    tabs = [t.to(dev, torch.bfloat16) for t in tabs]
+    g = torch.Generator().manual_seed(77)
+    wav_h = _pin((torch.randn(B, 72000, generator=g) * 0.1).clamp(-1, 1))
+    n_prefix, n_trail = 9, 24
+    text_h = _pin((torch.randn(B, n_prefix + 1 + 1 + REF_FRAMES + n_trail, H, generator=g) * 0.5).to(torch.bfloat16))
+    pad = (torch.randn(H, generator=g) * 0.1).to(torch.bfloat16).to(dev)
+    sp = q.SamplingParams(max_new_tokens=N + 1, suppress_eos=True, seed=4321, **spk)
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    runs = []
+    for it in range(3):
+        e = [ev() for _ in range(7)]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e[0].record()
+        wav = wav_h.to(dev, non_blocking=True)
+        text = text_h.to(dev, non_blocking=True)
+        ref = cenc.forward(wav)                                            # (B, 16, 38) codes
+        e[1].record()
+        xvec = senc.embed_waveform(wav).to(torch.bfloat16)                   # (B, H)
+        e[2].record()
+        R = ref.shape[-1]
+        icl = tabs[0][ref[:, 0, :].long()]
+        for j in range(1, G):
+            icl = icl + tabs[j][ref[:, j, :].long()]                       # (B, R, H): sum over the 16 codebooks
+        bos = tabs[0][torch.full((B, 1), cfg.talker.codec_bos_id, device=dev)]
+        rows = torch.cat([text[:, :n_prefix], xvec[:, None, :] + text[:, n_prefix:n_prefix + 1],
+                          text[:, n_prefix + 1:n_prefix + 2 + R] + torch.cat([bos, icl], dim=1)], dim=1)
+        trail = text[:, n_prefix + 2 + R:n_prefix + 2 + R + n_trail]
+        eng.ar.prefill([rows[b] for b in range(B)], [trail[b] for b in range(B)], pad, sp)
+        codes = torch.zeros(B, N, G, dtype=torch.int32, device=dev)
+        e[3].record()
+        eng.ar.decode(N, codes)
+        e[4].record()
+        full = torch.cat([ref.to(torch.int32), codes.transpose(1, 2)], dim=2)    # (B, 16, 38 + N)
+        wav_out = eng.codec.chunked_decode(full)
+        cut = int(REF_FRAMES / full.shape[-1] * wav_out.shape[-1])
+        e[5].record()
+        out_h = wav_out[..., cut:].contiguous().cpu()
+        e[6].record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1000.0
+        runs.append(([e[i].elapsed_time(e[i + 1]) for i in range(6)], wall, tuple(out_h.shape)))
+    st, wall, shape = runs[-1]
+    assert shape[0] == B and abs(shape[-1] - N * 1920) <= 1920, shape
+    return {"what": "config[4] voice clone, 1.7B-Base shape: 3 s prompt audio/row -> codec encode + x-vector + ICL prefill "
+                    f"({n_prefix + 2 + REF_FRAMES} rows + {n_trail} trailing) + {N} frame-steps + codec decode of {REF_FRAMES}+{N} frames + cut; "
+                    "host audio in, host audio out",
+            "batch": B, "frames": N, "ms_total_wall": wall,
+            "ms": dict(zip(("codec_encode", "x_vector", "icl_prefill", "ar_decode", "codec_decode", "d2h"), st)),
+            "frames_per_s": B * N / (wall / 1000.0), "rtf": (wall / 1000.0) / (B * N * FRAME_SEC),
+            "h2d_bytes": int(wav_h.numel() * 4 + text_h.numel() * 2), "d2h_bytes": int(B * shape[-1] * 4)}
+
+
 def hbm_peak():
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -430,7 +501,7 @@ def main():
     max_batch = max(args.batch, 32 if big else 1)
     max_ctx = max(lens) + args.frames + 8
     eng = TTSEngine(cfg, W, ccfg, CW, device=dev, max_batch=max_batch, max_ctx=max_ctx,
-                    codec_max_frames=max(args.frames + 8, 64))
+                    codec_max_frames=max(args.frames + 8 + (REF_FRAMES if big else 0), 64))
     sp = q.SamplingParams(max_new_tokens=args.frames + 1, suppress_eos=True, seed=1234, **spk)
     B, N, G = args.batch, args.frames, cfg.num_code_groups
     d_embs = [e.to(dev) for e in embs]
@@ -546,6 +617,20 @@ def main():
             assert len(w32) == 32
         except Exception as e:
             strong = {"error": repr(e)[:200]}
+        if 32 % world == 0:   # BASELINE config[4]: the voice-clone path at a global batch of 32 split over the N GPUs
+            vc, vc_err = None, None
+            try:
+                vc = voice_clone_probe(eng, q, cfg, W, args, spk, 32 // world, N, dev)
+            except Exception as e:
+                vc_err = repr(e)[:200]
+            vc_ms = parallel.max_over_ranks(vc["ms_total_wall"] if vc else 1e12, device=dev)   # every rank reaches this collective
+            if strong is None or "error" in strong:
+                strong = dict(strong or {})
+            if vc_ms >= 1e12:
+                strong["config4_voice_clone"] = {"error": vc_err or "failed on another rank"}
+            else:
+                strong["config4_voice_clone"] = {"global_batch": 32, "per_gpu_batch": 32 // world, "ms": vc_ms, "value": 32 * N / (vc_ms / 1e3),
+                                                 "unit": UNIT, "rank0_stages_ms": vc["ms"], "what": vc["what"]}
 
     tms = torch.tensor([ms_total, e2e_s * 1000.0, t_dec], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -602,7 +687,9 @@ def main():
         out["extras"] = {}
         for name, fn in (("batch1", lambda: decode_probe(eng, q, cfg, args, spk, 1, N, dev)),
                          ("batch32", lambda: decode_probe(eng, q, cfg, args, spk, 32, N, dev)),
-                         ("batch8_first_packet", lambda: {"first_packet_ms": first_packet_ms})):
+                         ("batch8_first_packet", lambda: {"first_packet_ms": first_packet_ms}),
+                         ("config4_voice_clone_batch4", lambda: voice_clone_probe(eng, q, cfg, W, args, spk, 4, N, dev)),
+                         ("config4_voice_clone_batch32", lambda: voice_clone_probe(eng, q, cfg, W, args, spk, 32, N, dev))):
             try:
                 out["extras"][name] = fn()
             except Exception as e:

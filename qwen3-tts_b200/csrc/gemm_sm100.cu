@@ -9,6 +9,9 @@
 //             arrive on tmem_empty when the accumulator has been read.
 #include "gemm_sm100.cuh"
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -89,6 +92,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+// sin for the SnakeBeta epilogue: Cody-Waite reduction to [-pi, pi] (k * 6.28125 is exact for |k| < 2^15), then the SFU
+// (MUFU.SIN, abs error 2^-21.4 on that interval).  The result is squared, scaled and rounded to bf16 (2^-9 relative), so
+// this is far inside the output's resolution for every argument below ~1e4; sinf()'s 20-instruction polynomial made
+// the epilogue of the short-K decoder convolutions as long as their mainloop.
+__device__ __forceinline__ float snake_sin(float a) {
+  const float k = rintf(a * 0.15915494309189535f);
+  float r = fmaf(-k, 6.28125f, a);
+  r = fmaf(-k, 1.9353071795864769e-3f, r);
+  return __sinf(r);
+}
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_constant__ GemmPlan p) {
   extern __shared__ unsigned char smem_raw[];
@@ -173,11 +187,25 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
     const int q = warp & 3;
     const int chalf = (warp - 2) >> 2;  // which 16-column chunk (mod EPI_WARPS/4) this warp takes
     int lt = 0;
+    // The k=1 convolutions of the residual units are memory-bound and each epilogue warp has one 32-byte residual read
+    // per row in flight: that is latency-, not bandwidth-limited.  Pull the NEXT tile's residual rows into L2 a whole
+    // tile ahead (no registers held), so the loads below are L2 hits.
+    auto prefetch_resid = [&](int t) {
+      if (!p.ep.resid || t >= total) return;
+      const int nt_ = t % ntiles, mt_ = (t / ntiles) % mtiles, b_ = t / (ntiles * mtiles);
+      const int m_ = mt_ * BM + q * 32 + lane;
+      if (m_ >= p.T) return;
+      const bf16* r = p.ep.resid + (size_t)b_ * (size_t)p.resid_bs + (size_t)m_ * (size_t)p.N + nt_ * p.bn;
+      for (int c0 = chalf * 16; c0 < p.bn; c0 += 16 * (EPI_WARPS / 4))
+        if (nt_ * p.bn + c0 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + c0));
+    };
+    prefetch_resid(blockIdx.x);
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
     const int acc = lt & 1;
     const int nt = tile % ntiles, mt = (tile / ntiles) % mtiles, b = tile / (ntiles * mtiles);
     const int m0 = mt * BM, n0 = nt * p.bn;
     const int m = m0 + q * 32 + lane;
+    prefetch_resid(tile + gridDim.x);
     mbar_wait(tfull0 + 8 * acc, (lt >> 1) & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tacc = tmem_base + (uint32_t)acc * acc_cols;
@@ -248,7 +276,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
           if (E.act == ACT_SNAKE) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float sn = sinf(x[i] * E.snake_ea[ch + i]);
+              const float sn = snake_sin(x[i] * E.snake_ea[ch + i]);
               y[i] = x[i] + E.snake_ib[ch + i] * sn * sn;
             }
           } else if (E.act == ACT_GELU) {
@@ -367,6 +395,10 @@ int gemm_pick_bn(int N, int mtiles, int B) {
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   const long long total = (long long)((plan.T + BM - 1) / BM) * ((plan.N + plan.bn - 1) / plan.bn) * plan.B;
   const int grid = (int)std::min<long long>(total, g_sm_count > 0 ? g_sm_count : 148);  // persistent: one CTA per SM walks the tiles
+  static const bool trace = getenv("Q3_GEMM_TRACE") != nullptr;  // tools/codec_breakdown.py joins this with an ncu launch list
+  if (trace)
+    fprintf(stderr, "[tap_gemm] B=%d T=%d N=%d Kp=%d taps=%d bn=%d tiles=%lld act=%d resid=%d\n", plan.B, plan.T, plan.N, plan.Kp,
+            plan.ntaps, plan.bn, total, plan.ep.act, plan.ep.resid ? 1 : 0);
   tap_gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(plan);
   Q3_CUDA(cudaGetLastError());
   return 0;

@@ -10,3 +10,6 @@ try:
 except Exception as e:
     print("bench failed", e); print(open("gpurun_out/bench_d.err").read()[-1500:])
 PY
+Q3_GEMM_TRACE=1 timeout 200 python tools/codec_breakdown.py --trace 2> gpurun_out/codec_trace.txt
+timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/codec_launches.csv python tools/codec_breakdown.py > /dev/null 2>&1
+python tools/codec_breakdown.py --join gpurun_out/codec_trace.txt gpurun_out/codec_launches.csv > gpurun_out/codec_breakdown.txt 2>&1; tail -5 gpurun_out/codec_breakdown.txt
