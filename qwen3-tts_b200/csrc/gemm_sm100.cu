@@ -17,15 +17,21 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B row
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;        // 16 KB
-constexpr int B_BYTES_MAX = 256 * BK * 2;   // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
+constexpr int SMEM_OPTIN = 232448;          // 227 KB
+// epilogue staging, per TMEM lane quadrant: X0, X1 (residual in / pre-activation out, alternating per step) and Y
+// (activated out), each 32 rows x 128 B (64 bf16 columns) with the 16-byte chunks XOR-swizzled by the row
+constexpr int EPI_BUF = 32 * 128;
+constexpr int EPI_Q_BYTES = 3 * EPI_BUF;
+constexpr int EPI_BYTES = 4 * EPI_Q_BYTES;  // 48 KB
+constexpr int BAR_BYTES = 256;              // full[S], empty[S], tmem_full[2], tmem_empty[2], tmem slot
 constexpr int EPI_WARPS = 16;                        // four per TMEM lane quadrant: the epilogue (tcgen05.ld + SnakeBeta / GELU /
                                                      // residual + stores) is what bounds the short-K convolutions (measured: 4 warps
                                                      // 28.5 ms, 8 warps 18.3 ms for the 8 x 125-frame codec)
 constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;    // producer warp, MMA warp, epilogue warps
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers: full[S], empty[S], tmem_full[2], tmem_empty[2], tmem slot*/;
+__host__ __device__ inline int stage_bytes_for(int bn) { return A_BYTES + ((bn * BK * 2 + 1023) & ~1023); }
+inline int stages_for(int bn) { return std::min(MAX_STAGES, (SMEM_OPTIN - 1024 - BAR_BYTES - EPI_BYTES) / stage_bytes_for(bn)); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -98,24 +104,57 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + er
 // this is far inside the output's resolution for every argument below ~1e4; sinf()'s 20-instruction polynomial made
 // the epilogue of the short-K decoder convolutions as long as their mainloop.
 __device__ __forceinline__ float snake_sin(float a) {
-  const float k = rintf(a * 0.15915494309189535f);
+  const float k = (fmaf(a, 0.15915494309189535f, 12582912.f)) - 12582912.f;  // rint for |a/2pi| < 2^22, on the FMA pipe (FRND is quarter-rate)
   float r = fmaf(-k, 6.28125f, a);
   r = fmaf(-k, 1.9353071795864769e-3f, r);
   return __sinf(r);
 }
 
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// 16 consecutive per-channel fp32 parameters (the channel index is a multiple of 16 and the vectors are 16-byte aligned)
+__device__ __forceinline__ void ldg16(const float* ptr, float (&o)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(ptr) + i);
+    o[4 * i] = t.x; o[4 * i + 1] = t.y; o[4 * i + 2] = t.z; o[4 * i + 3] = t.w;
+  }
+}
+
+// Round 16 values to bf16 and back (a PyTorch bf16 intermediate), two at a time through the packing convert
+// (F2FP.PACK_AB) — the scalar F2F.BF16.F32 goes through the quarter-rate XU pipe.  xp keeps the packed pairs.
+__device__ __forceinline__ void round16(float (&x)[16], uint32_t (&xp)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    xp[i] = pack_bf16(x[2 * i], x[2 * i + 1]);
+    x[2 * i] = bf16lo(xp[i]);
+    x[2 * i + 1] = bf16hi(xp[i]);
+  }
+}
+
+// ACT is a template parameter on purpose: with a run-time activation code ptxas if-converts the three activation
+// branches and evaluates erff() AND sin() for every element (measured: 55 instructions per output element).
+template <int ACT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_constant__ GemmPlan p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int STAGES = p.nst, STAGE_BYTES = stage_bytes_for(p.bn);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // full[S], empty[S], tmem_full[2], tmem_empty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  unsigned char* epi_smem = smem + STAGES * STAGE_BYTES + BAR_BYTES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kpb = p.Kp / BK;
   const int nkb = p.ntaps * kpb;
   const int mtiles = (p.T + BM - 1) / BM, ntiles = (p.N + p.bn - 1) / p.bn;
   const int total = mtiles * ntiles * p.B;
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull0 = smem_u32(bars + 2 * STAGES),
-                 tempty0 = smem_u32(bars + 2 * STAGES + 2);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + MAX_STAGES), tfull0 = smem_u32(bars + 2 * MAX_STAGES),
+                 tempty0 = smem_u32(bars + 2 * MAX_STAGES + 2);
   const uint32_t b_bytes = (uint32_t)p.bn * BK * 2;
   uint32_t acc_cols = 32;  // columns of one accumulator (power of two >= bn); two accumulators are allocated
   while (acc_cols < (uint32_t)p.bn) acc_cols <<= 1;
@@ -138,18 +177,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
 
   if (warp == 0) {
     if (lane == 0) {
-      int it = 0;  // k-blocks issued so far, over all tiles: ring position
+      int s = 0, round = 0;  // ring slot and how many times the ring has wrapped, over all tiles
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int nt = tile % ntiles, mt = (tile / ntiles) % mtiles, b = tile / (ntiles * mtiles);
         const int m0 = mt * BM, n0 = nt * p.bn;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % STAGES;
-          if (it >= STAGES) mbar_wait(empty0 + 8 * s, ((it / STAGES) - 1) & 1);
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (round > 0) mbar_wait(empty0 + 8 * s, (round - 1) & 1);
           const int tap = kb / kpb, k0 = (kb - tap * kpb) * BK;
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
           mbar_expect_tx(full0 + 8 * s, A_BYTES + b_bytes);
           tma_load_3d(sa, &p.tmA, k0, m0 + p.shift[tap] + p.a_row0, b, full0 + 8 * s);
           tma_load_2d(sb, &p.tmW, tap * p.Kp + k0, n0, full0 + 8 * s);
+          if (++s == STAGES) { s = 0; ++round; }
         }
       }
     }
@@ -157,7 +196,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N=bn, M=128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int it = 0, lt = 0;  // ring position; local tile counter (accumulator = lt & 1)
+      int s = 0, round = 0, lt = 0;  // ring position; local tile counter (accumulator = lt & 1)
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
         const int acc = lt & 1;
         if (lt >= 2) {  // the epilogue must have drained this accumulator (tile lt-2)
@@ -165,9 +204,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const uint32_t tacc = tmem_base + (uint32_t)acc * acc_cols;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(full0 + 8 * s, (it / STAGES) & 1);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full0 + 8 * s, round & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES), sb = sa + A_BYTES;
           const uint64_t ad = make_sdesc(sa), bd = make_sdesc(sb);
@@ -178,127 +216,185 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) tap_gemm_kernel(const __grid_
           }
           umma_commit(empty0 + 8 * s);                     // frees the smem slot once these MMAs have read it
           if (kb == nkb - 1) umma_commit(tfull0 + 8 * acc);  // accumulator complete
+          if (++s == STAGES) { s = 0; ++round; }
         }
       }
     }
   } else {
-    // ---- epilogue: warp (w % 4) owns TMEM lanes [32*(w%4), +32); thread = one output row; the two warps of a
-    // quadrant split the tile's columns (16-column chunks alternate) so the epilogue keeps up with short mainloops
+    // ---- epilogue.  Warp w owns TMEM lanes [32*(w%4), +32) (a hardware rule), one output row per thread; the four
+    // warps of a lane quadrant take the four 16-column chunks of one 64-column group per step.  Row-per-thread global
+    // accesses touch 32 different 128-byte lines per instruction, which made the LSU — not DRAM — the bound of the k=1
+    // convolutions (7-tap and 1-tap convolutions with the same output took the same time).  So the quadrant's 32 x 64
+    // bf16 block goes through a swizzled shared-memory buffer: residual rows arrive by coalesced cp.async one step
+    // ahead, results leave as 128-byte row segments (4 lines per store instruction instead of 32).
     const int q = warp & 3;
-    const int chalf = (warp - 2) >> 2;  // which 16-column chunk (mod EPI_WARPS/4) this warp takes
-    int lt = 0;
-    // The k=1 convolutions of the residual units are memory-bound and each epilogue warp has one 32-byte residual read
-    // per row in flight: that is latency-, not bandwidth-limited.  Pull the NEXT tile's residual rows into L2 a whole
-    // tile ahead (no registers held), so the loads below are L2 hits.
-    auto prefetch_resid = [&](int t) {
-      if (!p.ep.resid || t >= total) return;
-      const int nt_ = t % ntiles, mt_ = (t / ntiles) % mtiles, b_ = t / (ntiles * mtiles);
-      const int m_ = mt_ * BM + q * 32 + lane;
-      if (m_ >= p.T) return;
-      const bf16* r = p.ep.resid + (size_t)b_ * (size_t)p.resid_bs + (size_t)m_ * (size_t)p.N + nt_ * p.bn;
-      for (int c0 = chalf * 16; c0 < p.bn; c0 += 16 * (EPI_WARPS / 4))
-        if (nt_ * p.bn + c0 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + c0));
-    };
-    prefetch_resid(blockIdx.x);
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
-    const int acc = lt & 1;
-    const int nt = tile % ntiles, mt = (tile / ntiles) % mtiles, b = tile / (ntiles * mtiles);
-    const int m0 = mt * BM, n0 = nt * p.bn;
-    const int m = m0 + q * 32 + lane;
-    prefetch_resid(tile + gridDim.x);
-    mbar_wait(tfull0 + 8 * acc, (lt >> 1) & 1);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tacc = tmem_base + (uint32_t)acc * acc_cols;
+    const int j = (warp - 2) >> 2;           // 16-column chunk of the group
+    const int tq = j * 32 + lane;            // thread index inside the quadrant group (128 threads, named barrier 1+q)
     const GemmEpilogue& E = p.ep;
-    const bool row_ok = m < p.T;
-    const size_t mrow = (size_t)(row_ok ? m : 0) * (size_t)p.N;
-    const size_t raw_off = (size_t)b * (size_t)p.raw_bs + mrow, act_off = (size_t)b * (size_t)p.act_bs + mrow,
-                 res_off = (size_t)b * (size_t)p.resid_bs + mrow;
-    for (int c0 = chalf * 16; c0 < p.bn; c0 += 16 * (EPI_WARPS / 4)) {
-      uint32_t v[16];
-      tmem_ld16(tacc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const int n = n0 + c0;
-      if (!row_ok || n >= p.N) continue;
-      float x[16];
+    constexpr bool swiglu = ACT == ACT_SWIGLU_PAIR || ACT == ACT_SWIGLU_BLK8;
+    const uint32_t X0 = smem_u32(epi_smem + q * EPI_Q_BYTES);  // X[k] = X0 + k * EPI_BUF (shared-space addresses)
+    const uint32_t Y = X0 + 2 * EPI_BUF;
+    const int ngroups = (p.bn + 63) >> 6;
+    // the two 16-byte items of the quadrant block this thread moves in the cooperative (coalesced) copies
+    const int it_row0 = tq >> 3, it_chunk = tq & 7;  // second item: row + 16
+    // own slots (row = lane): chunks 2j and 2j+1
+    const uint32_t own0 = (uint32_t)lane * 128u + (uint32_t)(((2 * j) ^ (lane & 7)) << 4),
+                   own1 = (uint32_t)lane * 128u + (uint32_t)(((2 * j + 1) ^ (lane & 7)) << 4);
+    auto qbar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + q) : "memory"); };
+    auto tile_coords = [&](int t, int& b_, int& m0_, int& n0_) {
+      const int nt_ = t % ntiles, mt_ = (t / ntiles) % mtiles;
+      b_ = t / (ntiles * mtiles); m0_ = mt_ * BM; n0_ = nt_ * p.bn;
+    };
+    // coalesced residual fetch of group g of the tile at (b_, m0_, n0_) into buffer `dst`; always commits a group
+    auto issue_resid = [&](bool valid, int b_, int m0_, int n0_, int g, uint32_t dst) {
+      const int col = g * 64 + it_chunk * 8;
+      if (valid && col < p.bn && n0_ + col < p.N) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
-      int ch = n % E.cmod;
-      if (E.bias) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] += E.bias[ch + i];
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i) x[i] = rbf(x[i]);  // the reference's layer output is bf16
-      if (E.scale) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x[i] = rbf(x[i] * E.scale[ch + i]);
-      }
-      if (E.resid) {
-        const uint4 r0 = *reinterpret_cast<const uint4*>(E.resid + res_off + n);
-        const uint4 r1 = *reinterpret_cast<const uint4*>(E.resid + res_off + n + 8);
-        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { x[2 * i] = rbf(x[2 * i] + bf16lo(rr[i])); x[2 * i + 1] = rbf(x[2 * i + 1] + bf16hi(rr[i])); }
-      }
-      if (E.out_raw) {
-        uint4 o0, o1;
-        o0.x = pack_bf16(x[0], x[1]); o0.y = pack_bf16(x[2], x[3]); o0.z = pack_bf16(x[4], x[5]); o0.w = pack_bf16(x[6], x[7]);
-        o1.x = pack_bf16(x[8], x[9]); o1.y = pack_bf16(x[10], x[11]); o1.z = pack_bf16(x[12], x[13]); o1.w = pack_bf16(x[14], x[15]);
-        *reinterpret_cast<uint4*>(E.out_raw + raw_off + n) = o0;
-        *reinterpret_cast<uint4*>(E.out_raw + raw_off + n + 8) = o1;
-      }
-      if (E.out_act) {
-        if (E.act == ACT_SWIGLU_BLK8) {
-          // 16 columns = gate[8j..8j+7] | up[8j..8j+7] (the AR engine's gate_up row interleave); out is [..][N/2]
-          float y[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float g = x[i], u = x[8 + i];
-            y[i] = rbf(g / (1.f + __expf(-g))) * u;
+        for (int i = 0; i < 2; ++i) {
+          const int r = it_row0 + 16 * i, m_ = m0_ + q * 32 + r;
+          if (m_ < p.T) {
+            const bf16* src = E.resid + (size_t)b_ * (size_t)p.resid_bs + (size_t)m_ * (size_t)p.N + n0_ + col;
+            const uint32_t d = dst + r * 128 + ((it_chunk ^ (r & 7)) << 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
           }
-          uint4 o;
-          o.x = pack_bf16(y[0], y[1]); o.y = pack_bf16(y[2], y[3]); o.z = pack_bf16(y[4], y[5]); o.w = pack_bf16(y[6], y[7]);
-          *reinterpret_cast<uint4*>(E.out_act + (size_t)b * (size_t)p.act_bs + (size_t)m * (size_t)(p.N / 2) + n / 2) = o;
-        } else if (E.act == ACT_SWIGLU_PAIR) {
-          // columns (2i, 2i+1) = (gate_i, up_i)
-          float y[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float g = x[2 * i], u = x[2 * i + 1];
-            y[i] = rbf(g / (1.f + __expf(-g))) * u;
-          }
-          uint4 o;
-          o.x = pack_bf16(y[0], y[1]); o.y = pack_bf16(y[2], y[3]); o.z = pack_bf16(y[4], y[5]); o.w = pack_bf16(y[6], y[7]);
-          *reinterpret_cast<uint4*>(E.out_act + (size_t)b * (size_t)p.act_bs + (size_t)m * (size_t)(p.N / 2) + n / 2) = o;
-        } else {
-          float y[16];
-          if (E.act == ACT_SNAKE) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float sn = snake_sin(x[i] * E.snake_ea[ch + i]);
-              y[i] = x[i] + E.snake_ib[ch + i] * sn * sn;
-            }
-          } else if (E.act == ACT_GELU) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) y[i] = gelu_erf(x[i]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) y[i] = x[i];
-          }
-          uint4 o0, o1;
-          o0.x = pack_bf16(y[0], y[1]); o0.y = pack_bf16(y[2], y[3]); o0.z = pack_bf16(y[4], y[5]); o0.w = pack_bf16(y[6], y[7]);
-          o1.x = pack_bf16(y[8], y[9]); o1.y = pack_bf16(y[10], y[11]); o1.z = pack_bf16(y[12], y[13]); o1.w = pack_bf16(y[14], y[15]);
-          *reinterpret_cast<uint4*>(E.out_act + act_off + n) = o0;
-          *reinterpret_cast<uint4*>(E.out_act + act_off + n + 8) = o1;
         }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto store_rows = [&](uint32_t src, bf16* out, long long bs, int b_, int m0_, int n0_, int g) {
+      const int col = g * 64 + it_chunk * 8;
+      if (col >= p.bn || n0_ + col >= p.N) return;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int r = it_row0 + 16 * i, m_ = m0_ + q * 32 + r;
+        if (m_ < p.T) {
+          const uint4 v = lds128(src + r * 128 + ((it_chunk ^ (r & 7)) << 4));
+          *reinterpret_cast<uint4*>(out + (size_t)b_ * (size_t)bs + (size_t)m_ * (size_t)p.N + n0_ + col) = v;
+        }
+      }
+    };
+    int lt = 0, step = 0;
+    int b = 0, m0 = 0, n0 = 0, nb = 0, nm0 = 0, nn0 = 0;  // this tile's and the next tile's coordinates (the divisions happen once per tile)
+    if ((int)blockIdx.x < total) tile_coords(blockIdx.x, nb, nm0, nn0);
+    if (!swiglu && E.resid) issue_resid((int)blockIdx.x < total, nb, nm0, nn0, 0, X0);
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+    const int acc = lt & 1;
+    b = nb; m0 = nm0; n0 = nn0;
+    const bool more = tile + (int)gridDim.x < total;
+    if (more) tile_coords(tile + gridDim.x, nb, nm0, nn0);
+    const int m = m0 + q * 32 + lane;
+    const bool row_ok = m < p.T;
+    mbar_wait(tfull0 + 8 * acc, (lt >> 1) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tacc = tmem_base + (uint32_t)acc * acc_cols + ((uint32_t)(q * 32) << 16);
+    if constexpr (swiglu) {
+      // gated-MLP epilogues (transformer layers only, T = frames): halves the width, written directly
+      for (int c0 = j * 16; c0 < p.bn; c0 += 64) {
+        uint32_t v[16];
+        tmem_ld16(tacc + (uint32_t)c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int n = n0 + c0;
+        if (!row_ok || n >= p.N) continue;
+        float x[16];
+        const int ch = n % E.cmod;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = rbf(__uint_as_float(v[i]) + (E.bias ? E.bias[ch + i] : 0.f));
+        float y[8];
+        if constexpr (ACT == ACT_SWIGLU_BLK8) {  // 16 columns = gate[8j..8j+7] | up[8j..8j+7] (the AR engine's gate_up row interleave)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const float gt = x[i], u = x[8 + i]; y[i] = rbf(gt / (1.f + __expf(-gt))) * u; }
+        } else {                         // columns (2i, 2i+1) = (gate_i, up_i)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const float gt = x[2 * i], u = x[2 * i + 1]; y[i] = rbf(gt / (1.f + __expf(-gt))) * u; }
+        }
+        uint4 o;
+        o.x = pack_bf16(y[0], y[1]); o.y = pack_bf16(y[2], y[3]); o.z = pack_bf16(y[4], y[5]); o.w = pack_bf16(y[6], y[7]);
+        *reinterpret_cast<uint4*>(E.out_act + (size_t)b * (size_t)p.act_bs + (size_t)m * (size_t)(p.N / 2) + n / 2) = o;
+      }
+    } else {
+      uint32_t v[16];
+      for (int g = 0; g < ngroups; ++g, ++step) {
+        const uint32_t Xc = X0 + (step & 1) * EPI_BUF;
+        const int c0 = g * 64 + j * 16, n = n0 + c0;
+        const bool have = c0 < p.bn && n < p.N;
+        if (g == 0 && have) tmem_ld16(tacc + (uint32_t)c0, v);  // later groups were requested a step ahead (below)
+        if (E.resid) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (have) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        qbar();  // residual block visible to the quadrant; the previous step's row stores have left X[step^1] and Y
+        if (E.resid) {
+          if (g + 1 < ngroups) issue_resid(true, b, m0, n0, g + 1, X0 + ((step + 1) & 1) * EPI_BUF);
+          else issue_resid(more, nb, nm0, nn0, 0, X0 + ((step + 1) & 1) * EPI_BUF);
+        }
+        float x[16];
+        if (have) {  // warp-uniform: tcgen05.ld is .sync.aligned
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
+          if (c0 + 64 < p.bn && n + 64 < p.N) tmem_ld16(tacc + (uint32_t)(c0 + 64), v);  // next group's accumulator chunk: in flight during the math
+        }
+        if (have && row_ok) {
+          const int ch = n % E.cmod;
+          if (E.bias) {
+            float bv[16];
+            ldg16(E.bias + ch, bv);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] += bv[i];
+          }
+          uint32_t xp[8];
+          round16(x, xp);  // the reference's layer output is bf16
+          if (E.scale) {
+            float sv[16];
+            ldg16(E.scale + ch, sv);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] *= sv[i];
+            round16(x, xp);
+          }
+          if (E.resid) {
+            const uint4 r0 = lds128(Xc + own0), r1 = lds128(Xc + own1);
+            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { x[2 * i] += bf16lo(rr[i]); x[2 * i + 1] += bf16hi(rr[i]); }
+            round16(x, xp);
+          }
+          if (E.out_raw) {
+            sts128(Xc + own0, make_uint4(xp[0], xp[1], xp[2], xp[3]));
+            sts128(Xc + own1, make_uint4(xp[4], xp[5], xp[6], xp[7]));
+          }
+          if (E.out_act) {
+            float y[16];
+            if constexpr (ACT == ACT_SNAKE) {
+              float ea[16], ib[16];
+              ldg16(E.snake_ea + ch, ea);
+              ldg16(E.snake_ib + ch, ib);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float sn = snake_sin(x[i] * ea[i]);
+                y[i] = x[i] + ib[i] * sn * sn;
+              }
+            } else if constexpr (ACT == ACT_GELU) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) y[i] = gelu_erf(x[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) y[i] = x[i];
+            }
+            uint4 o0, o1;
+            o0.x = pack_bf16(y[0], y[1]); o0.y = pack_bf16(y[2], y[3]); o0.z = pack_bf16(y[4], y[5]); o0.w = pack_bf16(y[6], y[7]);
+            o1.x = pack_bf16(y[8], y[9]); o1.y = pack_bf16(y[10], y[11]); o1.z = pack_bf16(y[12], y[13]); o1.w = pack_bf16(y[14], y[15]);
+            sts128(Y + own0, o0);
+            sts128(Y + own1, o1);
+          }
+        }
+        qbar();  // the quadrant's block is complete in shared memory
+        if (E.out_raw) store_rows(Xc, E.out_raw, p.raw_bs, b, m0, n0, g);
+        if (E.out_act) store_rows(Y, E.out_act, p.act_bs, b, m0, n0, g);
+      }
     }
-    // this warp has read its 32 lanes of the accumulator: hand it back to the MMA issuer (one arrival per epilogue warp)
+    // this warp has read its part of the accumulator: hand it back to the MMA issuer (one arrival per epilogue warp)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncwarp();
     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty0 + 8 * acc) : "memory");
     }  // tile loop
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -324,7 +420,11 @@ int gemm_init() {
     Q3_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
     g_encode = reinterpret_cast<EncodeFn>(fn);
   }
-  Q3_CUDA(cudaFuncSetAttribute(tap_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+  Q3_CUDA(cudaFuncSetAttribute(tap_gemm_kernel<ACT_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPTIN));
+  Q3_CUDA(cudaFuncSetAttribute(tap_gemm_kernel<ACT_SNAKE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPTIN));
+  Q3_CUDA(cudaFuncSetAttribute(tap_gemm_kernel<ACT_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPTIN));
+  Q3_CUDA(cudaFuncSetAttribute(tap_gemm_kernel<ACT_SWIGLU_PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPTIN));
+  Q3_CUDA(cudaFuncSetAttribute(tap_gemm_kernel<ACT_SWIGLU_BLK8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPTIN));
   if (g_sm_count == 0) {
     int dev = 0;
     Q3_CUDA(cudaGetDevice(&dev));
@@ -345,11 +445,17 @@ int gemm_make_plan_v(GemmPlan* plan, const bf16* a, int B, int T, int K, int64_t
   Q3_REQUIRE(bn % 16 == 0 && bn >= 16 && bn <= 256, "bn must be a multiple of 16 in [16,256]");
   Q3_REQUIRE(N % 16 == 0, "N must be a multiple of 16");
   Q3_REQUIRE(ntaps >= 1 && ntaps <= 8, "ntaps out of range");
+  Q3_REQUIRE(ep.cmod % 16 == 0 && ((uintptr_t)ep.bias % 16) == 0 && ((uintptr_t)ep.scale % 16) == 0 &&
+                 ((uintptr_t)ep.snake_ea % 16) == 0 && ((uintptr_t)ep.snake_ib % 16) == 0,
+             "per-channel epilogue vectors must be 16-byte aligned and the channel count a multiple of 16");
+  Q3_REQUIRE(!((ep.act == ACT_SWIGLU_PAIR || ep.act == ACT_SWIGLU_BLK8) && (ep.resid || ep.out_raw || ep.scale)),
+             "gated epilogues write out_act only");
   Q3_REQUIRE((lda * 2) % 16 == 0 && (a_batch_stride * 2) % 16 == 0 && ((uintptr_t)a % 16) == 0, "A alignment");
   memset(plan, 0, sizeof(*plan));
   plan->B = B; plan->T = T; plan->N = N; plan->Kp = Kp; plan->ntaps = ntaps; plan->bn = bn; plan->ep = ep;
   const bool half = ep.act == ACT_SWIGLU_PAIR || ep.act == ACT_SWIGLU_BLK8;
   plan->a_row0 = v.a_row0;
+  plan->nst = stages_for(bn);
   plan->raw_bs = v.raw_bs ? v.raw_bs : (long long)T * N;
   plan->act_bs = v.act_bs ? v.act_bs : (long long)T * (half ? N / 2 : N);
   plan->resid_bs = v.resid_bs ? v.resid_bs : (long long)T * N;
@@ -399,7 +505,15 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   if (trace)
     fprintf(stderr, "[tap_gemm] B=%d T=%d N=%d Kp=%d taps=%d bn=%d tiles=%lld act=%d resid=%d\n", plan.B, plan.T, plan.N, plan.Kp,
             plan.ntaps, plan.bn, total, plan.ep.act, plan.ep.resid ? 1 : 0);
-  tap_gemm_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(plan);
+  const int smem_bytes = 1024 + plan.nst * stage_bytes_for(plan.bn) + BAR_BYTES + EPI_BYTES;
+  switch (plan.ep.act) {
+    case ACT_NONE: tap_gemm_kernel<ACT_NONE><<<grid, GEMM_THREADS, smem_bytes, stream>>>(plan); break;
+    case ACT_SNAKE: tap_gemm_kernel<ACT_SNAKE><<<grid, GEMM_THREADS, smem_bytes, stream>>>(plan); break;
+    case ACT_GELU: tap_gemm_kernel<ACT_GELU><<<grid, GEMM_THREADS, smem_bytes, stream>>>(plan); break;
+    case ACT_SWIGLU_PAIR: tap_gemm_kernel<ACT_SWIGLU_PAIR><<<grid, GEMM_THREADS, smem_bytes, stream>>>(plan); break;
+    case ACT_SWIGLU_BLK8: tap_gemm_kernel<ACT_SWIGLU_BLK8><<<grid, GEMM_THREADS, smem_bytes, stream>>>(plan); break;
+    default: Q3_REQUIRE(false, "unknown activation %d", plan.ep.act);
+  }
   Q3_CUDA(cudaGetLastError());
   return 0;
 }

@@ -26,6 +26,7 @@ struct GemmEpilogue {
 struct GemmPlan {
   CUtensorMap tmA, tmW;
   int B, T, N, Kp, ntaps, bn;
+  int nst;                          // depth of the TMA ring (4, or 3 for the widest tiles: the epilogue staging needs 48 KB)
   int shift[8];
   int a_row0;                       // added to every A row coordinate (history-prefixed inputs of the streaming codec)
   long long raw_bs, act_bs, resid_bs;  // batch strides (elements) of out_raw / out_act / resid; rows are N (N/2) wide

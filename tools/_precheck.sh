@@ -1,6 +1,6 @@
 set -u
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests/test_gpu_codec.py tests/test_gpu_codec_stream.py tests/test_gpu_e2e.py -x -q > gpurun_out/t_codec.log 2>&1; tail -3 gpurun_out/t_codec.log
+timeout 600 python -m pytest tests/test_gpu_codec.py tests/test_gpu_codec_stream.py tests/test_gpu_e2e.py tests/test_gpu_ar.py -k "not full_shape" -x -q > gpurun_out/t_codec.log 2>&1; tail -3 gpurun_out/t_codec.log
 timeout 200 python bench.py --steps 2 --warmup 1 --no-extras --no-cpu-baseline --no-parity-check > gpurun_out/bench_d.json 2> gpurun_out/bench_d.err
 python - <<PY
 import json
