@@ -384,7 +384,7 @@ def voice_clone_probe(eng, q, cfg, W, args, spk, B, N, dev):
         icl = tabs[0][ref[:, 0, :].long()]
         for j in range(1, G):
             icl = icl + tabs[j][ref[:, j, :].long()]                       # (B, R, H): sum over the 16 codebooks
-        bos = tabs[0][torch.full((B, 1), cfg.talker.codec_bos_id, device=dev)]
+        bos = tabs[0][torch.full((B, 1), cfg.codec_bos_id, device=dev)]
         rows = torch.cat([text[:, :n_prefix], xvec[:, None, :] + text[:, n_prefix:n_prefix + 1],
                           text[:, n_prefix + 1:n_prefix + 2 + R] + torch.cat([bos, icl], dim=1)], dim=1)
         trail = text[:, n_prefix + 2 + R:n_prefix + 2 + R + n_trail]
