@@ -50,7 +50,7 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // the persistent kernel
 // ------------------------------------------------------------------------------------------------
-template <int NT>
+template <int NT, bool HID>
 __global__ void __launch_bounds__(CTA_THREADS, 1) q3_step_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ Phase s_ph[2];
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) q3_step_kernel(const __grid_co
         PROF_MARK(6);
       }
       const int type = ph.type;
-      if (type == PH_GEMV) xpar = gemv_phase<NT>(ph, meta[pi], P, rg, smem, &s_tab, xbar, xpar, pol_stream, pol_keep, frame);
+      if (type == PH_GEMV) xpar = gemv_phase<NT, HID>(ph, meta[pi], P, rg, smem, &s_tab, xbar, xpar, pol_stream, pol_keep, frame);
       else if (type == PH_ATTN) attn_phase(ph, P, smem + P.plan.x_off, frame);
       else sample_phase(ph, P, smem + P.plan.x_off, frame, P.mode == 0);
       if (dhave) reinterpret_cast<uint32_t*>(&s_ph[slot ^ 1])[tid] = dreg;
@@ -683,15 +683,15 @@ extern "C" int q3_engine_finalize(q3_engine* e) {
   // kernel attributes: all opt-in shared memory minus the kernel's static part is the dynamic budget of the plans
   {
     int stat = 0;
-    for (const void* fn : {(const void*)q3_step_kernel<1>, (const void*)q3_step_kernel<2>, (const void*)q3_step_kernel<4>}) {
+    const void* fns[] = {(const void*)q3_step_kernel<1, false>, (const void*)q3_step_kernel<2, false>, (const void*)q3_step_kernel<4, false>,
+                         (const void*)q3_step_kernel<1, true>,  (const void*)q3_step_kernel<2, true>,  (const void*)q3_step_kernel<4, true>};
+    for (const void* fn : fns) {
       cudaFuncAttributes fa;
       Q3_CUDA(cudaFuncGetAttributes(&fa, fn));
       stat = std::max(stat, (int)fa.sharedSizeBytes);
     }
     e->max_dyn_smem = SMEM_OPTIN - (stat + 127) / 128 * 128;
-    Q3_CUDA(cudaFuncSetAttribute(q3_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_dyn_smem));
-    Q3_CUDA(cudaFuncSetAttribute(q3_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_dyn_smem));
-    Q3_CUDA(cudaFuncSetAttribute(q3_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_dyn_smem));
+    for (const void* fn : fns) Q3_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, e->max_dyn_smem));
   }
   {  // weight arena base for the 32-bit (x16 B) offsets of the phase metas
     const char *lo = nullptr, *hi = nullptr;
@@ -748,8 +748,10 @@ static int launch_program(q3_engine* e, int off, int n, int mode, int max_iters,
   Q3_REQUIRE(n <= MAX_PHASES, "program of %d phases exceeds %d", n, MAX_PHASES);
   Q3_CUDA(cudaMemsetAsync(&e->st->bar_count, 0, sizeof(unsigned int) * (1 + 256), stream));  // counter + per-CTA flags
   void* args[] = {&P};
-  const void* fn = nt == 1 ? (const void*)q3_step_kernel<1> : nt == 2 ? (const void*)q3_step_kernel<2>
-                                                                     : (const void*)q3_step_kernel<4>;
+  const void* fn = P.hid_out ? (nt == 1 ? (const void*)q3_step_kernel<1, true> : nt == 2 ? (const void*)q3_step_kernel<2, true>
+                                                                                           : (const void*)q3_step_kernel<4, true>)
+                             : (nt == 1 ? (const void*)q3_step_kernel<1, false> : nt == 2 ? (const void*)q3_step_kernel<2, false>
+                                                                                            : (const void*)q3_step_kernel<4, false>);
   Q3_CUDA(cudaLaunchCooperativeKernel(fn, dim3(e->sm_count), dim3(CTA_THREADS), args, (size_t)plan.total, stream));
   return 0;
 }
