@@ -97,6 +97,7 @@ __device__ __forceinline__ void attn_prefetch(const Phase& ph, const KParams& P,
   attn_window_issue(ph, P, smem, frame, (int)blockIdx.x);
 }
 
+template <bool DEV>
 __device__ __forceinline__ void attn_phase(const Phase& ph, const KParams& P, unsigned char* smem, int frame) {
   const StackDev& S = ph.stack == 0 ? P.talker : P.cp;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

@@ -50,14 +50,17 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 // the persistent kernel
 // ------------------------------------------------------------------------------------------------
-template <int NT, bool HID>
+// VAR: 0 = production, 1 = production + per-step hidden-state capture, 2 = development (hidden capture + device-timestamp
+// marks + the ablation / A-B knobs of KParams::flags).  See gemv_phase for why these are separate instantiations.
+template <int NT, int VAR>
 __global__ void __launch_bounds__(CTA_THREADS, 1) q3_step_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ Phase s_ph[2];
   __shared__ RoundTab s_tab;
   DevState* st = P.st;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool use_counter = (P.flags & 1) == 0;
+  constexpr bool HID = VAR >= 1, DEV = VAR == 2;
+  const bool use_counter = !DEV || (P.flags & 1) == 0;
   unsigned int epoch = 0;  // host resets bar_count / bar_flags to 0 before every launch
   PMeta* meta = reinterpret_cast<PMeta*>(smem + P.plan.meta_off);
   const int R = P.plan.nslots, SB = P.plan.slot_blocks;
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) q3_step_kernel(const __grid_co
     ring_init(rg, P.runs + o0, (int)(o1 - o0), (long long)(o1 - o0) * niter);
   }
 #pragma unroll 1
-  for (int i = 0; i < R; ++i) ring_issue(rg, P, lane, pol_stream, pol_keep);
+  for (int i = 0; i < R; ++i) ring_issue<DEV>(rg, P, lane, pol_stream, pol_keep);
   __syncthreads();
 
   const int step_base = st->step;
@@ -138,12 +141,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) q3_step_kernel(const __grid_co
       if (dhave) dreg = reinterpret_cast<const uint32_t*>(P.prog + nx)[tid];
       const Phase& ph = s_ph[slot];
       if (tid == 0) {
-        g_prof_row = (P.prof && it == 0) ? P.prof + ((size_t)pi * gridDim.x + blockIdx.x) * 16 : nullptr;
+        if constexpr (DEV) g_prof_row = (P.prof && it == 0) ? P.prof + ((size_t)pi * gridDim.x + blockIdx.x) * 16 : nullptr;
         PROF_MARK(6);
       }
       const int type = ph.type;
-      if (type == PH_GEMV) xpar = gemv_phase<NT, HID>(ph, meta[pi], P, rg, smem, &s_tab, xbar, xpar, pol_stream, pol_keep, frame);
-      else if (type == PH_ATTN) attn_phase(ph, P, smem + P.plan.x_off, frame);
+      if (type == PH_GEMV) xpar = gemv_phase<NT, HID, DEV>(ph, meta[pi], P, rg, smem, &s_tab, xbar, xpar, pol_stream, pol_keep, frame);
+      else if (type == PH_ATTN) attn_phase<DEV>(ph, P, smem + P.plan.x_off, frame);
       else sample_phase(ph, P, smem + P.plan.x_off, frame, P.mode == 0);
       if (dhave) reinterpret_cast<uint32_t*>(&s_ph[slot ^ 1])[tid] = dreg;
       cta_sync();  // body done (global writes of every thread precede thread 0's release), next descriptor visible
@@ -683,8 +686,9 @@ extern "C" int q3_engine_finalize(q3_engine* e) {
   // kernel attributes: all opt-in shared memory minus the kernel's static part is the dynamic budget of the plans
   {
     int stat = 0;
-    const void* fns[] = {(const void*)q3_step_kernel<1, false>, (const void*)q3_step_kernel<2, false>, (const void*)q3_step_kernel<4, false>,
-                         (const void*)q3_step_kernel<1, true>,  (const void*)q3_step_kernel<2, true>,  (const void*)q3_step_kernel<4, true>};
+    const void* fns[] = {(const void*)q3_step_kernel<1, 0>, (const void*)q3_step_kernel<2, 0>, (const void*)q3_step_kernel<4, 0>,
+                         (const void*)q3_step_kernel<1, 1>, (const void*)q3_step_kernel<2, 1>, (const void*)q3_step_kernel<4, 1>,
+                         (const void*)q3_step_kernel<1, 2>, (const void*)q3_step_kernel<2, 2>, (const void*)q3_step_kernel<4, 2>};
     for (const void* fn : fns) {
       cudaFuncAttributes fa;
       Q3_CUDA(cudaFuncGetAttributes(&fa, fn));
@@ -748,10 +752,12 @@ static int launch_program(q3_engine* e, int off, int n, int mode, int max_iters,
   Q3_REQUIRE(n <= MAX_PHASES, "program of %d phases exceeds %d", n, MAX_PHASES);
   Q3_CUDA(cudaMemsetAsync(&e->st->bar_count, 0, sizeof(unsigned int) * (1 + 256), stream));  // counter + per-CTA flags
   void* args[] = {&P};
-  const void* fn = P.hid_out ? (nt == 1 ? (const void*)q3_step_kernel<1, true> : nt == 2 ? (const void*)q3_step_kernel<2, true>
-                                                                                           : (const void*)q3_step_kernel<4, true>)
-                             : (nt == 1 ? (const void*)q3_step_kernel<1, false> : nt == 2 ? (const void*)q3_step_kernel<2, false>
-                                                                                            : (const void*)q3_step_kernel<4, false>);
+  const int var = (P.flags != 0 || P.prof) ? 2 : P.hid_out ? 1 : 0;
+  static const void* const kfn[3][3] = {
+      {(const void*)q3_step_kernel<1, 0>, (const void*)q3_step_kernel<2, 0>, (const void*)q3_step_kernel<4, 0>},
+      {(const void*)q3_step_kernel<1, 1>, (const void*)q3_step_kernel<2, 1>, (const void*)q3_step_kernel<4, 1>},
+      {(const void*)q3_step_kernel<1, 2>, (const void*)q3_step_kernel<2, 2>, (const void*)q3_step_kernel<4, 2>}};
+  const void* fn = kfn[var][nt == 1 ? 0 : nt == 2 ? 1 : 2];
   Q3_CUDA(cudaLaunchCooperativeKernel(fn, dim3(e->sm_count), dim3(CTA_THREADS), args, (size_t)plan.total, stream));
   return 0;
 }

@@ -75,9 +75,10 @@ __device__ __forceinline__ void cta_sync() { __syncthreads(); }
 
 // fine-grained profiling marks (thread 0 only, first frame of a profiled launch)
 __shared__ unsigned long long* g_prof_row;
+// (compiled only into the development instantiation: a constexpr bool DEV must be in scope)
 #define PROF_MARK(k)                                                                   \
   do {                                                                                 \
-    if (threadIdx.x == 0 && g_prof_row) {                                              \
+    if constexpr (DEV) if (threadIdx.x == 0 && g_prof_row) {                           \
       unsigned long long _t;                                                           \
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                          \
       g_prof_row[k] = _t;                                                              \
@@ -173,6 +174,7 @@ __device__ __forceinline__ void ring_init(Ring& rg, const uint2* list, int len, 
 }
 
 // request the next piece (<= SB blocks of the current run) into slot p_slot; lane 0 issues, every lane keeps the books
+template <bool DEV>
 __device__ __forceinline__ void ring_issue(Ring& rg, const KParams& P, int lane, uint64_t pol_stream, uint64_t pol_keep) {
   if (rg.cur_left == 0) {
     if (rg.runs_left <= 0) return;
@@ -191,7 +193,7 @@ __device__ __forceinline__ void ring_issue(Ring& rg, const KParams& P, int lane,
     // address-hashed fraction evict_last (the code predictor's layer weights are re-read on each of its 15 passes:
     // what stays in L2 is not re-fetched from HBM; measured traffic: profiles/r02_l2_residency.txt)
     const uint64_t pol = rg.cur_keep ? pol_keep : pol_stream;
-    if (P.flags & 4) bulk_g2s_plain(rg.slots + (uint32_t)(rg.p_slot * rg.SB) * 1024u, src, bytes, bar);
+    if (DEV && (P.flags & 4)) bulk_g2s_plain(rg.slots + (uint32_t)(rg.p_slot * rg.SB) * 1024u, src, bytes, bar);
     else bulk_g2s(rg.slots + (uint32_t)(rg.p_slot * rg.SB) * 1024u, src, bytes, bar, pol);
   }
   rg.cur_off += (uint32_t)nb << 6;
@@ -200,11 +202,12 @@ __device__ __forceinline__ void ring_issue(Ring& rg, const KParams& P, int lane,
   ++rg.outstanding;
 }
 
+template <bool DEV>
 __device__ __forceinline__ void ring_release(Ring& rg, const KParams& P, int lane, uint64_t pol_stream, uint64_t pol_keep) {
   __syncwarp();  // every lane's reads of the slot are done before the async proxy overwrites it
   if (++rg.c_slot == rg.R) { rg.c_slot = 0; rg.c_par ^= 1; }
   --rg.outstanding;
-  ring_issue(rg, P, lane, pol_stream, pol_keep);
+  ring_issue<DEV>(rg, P, lane, pol_stream, pol_keep);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -371,8 +374,9 @@ __device__ __forceinline__ void flush_acc(float (&acc)[NACC][NT][4], float* pp, 
 // The phase body.  `m` is this CTA's meta of the phase (tiles owned, K blocks); the weights arrive through the ring.
 // HID: the kernel instantiation that also captures the per-step hidden states (generate(return_hidden=True)); the
 // default instantiation does not carry that code — the phase loop's instruction footprint is a first-order term
-// (measured: 4.22 -> 4.14 ms per frame-step at B=8 without it).
-template <int NT, bool HID>
+// (measured: 4.22 -> 4.14 ms per frame-step at B=8 without it).  DEV: the development instantiation with the
+// device-timestamp marks and the ablation / A-B knobs of KParams::flags; production kernels carry none of it.
+template <int NT, bool HID, bool DEV>
 __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, const KParams& P, Ring& rg, unsigned char* smem,
                                                RoundTab* tab, uint32_t xbar, uint32_t xpar, uint64_t pol_stream, uint64_t pol_keep, int frame) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -396,7 +400,7 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
   const uint32_t xs_sh = smem_addr(xs);
 
   // ---- activations -> shared memory
-  if (staged && (ntc > 0 || save) && !(P.flags & 32)) {
+  if (staged && (ntc > 0 || save) && !(DEV && (P.flags & 32))) {
     if (normed) {
       stage_columns(src, src_ld, ph.eps, save, P.mode == 0 ? P.admit_mask : 0xffffffffu, K, nc, xs, xstride, nw_s,
                     (HID && save) ? P.hid_out : nullptr, P.hid_stride, P.mode == 0 ? 0 : frame + 1, P.frame0);
@@ -484,11 +488,11 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
           load_bfrags<NT>(bnx, gsrc, src_ld, nc - g, nct, kn, KB);
         }
         long long w0 = 0;
-        if (g_prof_row) w0 = clock64();
+        if (DEV && g_prof_row) w0 = clock64();
         mbar_wait(rg.full + 8u * rg.c_slot, (uint32_t)rg.c_par, P.st);
-        if (g_prof_row && tid == 0) wait_cycles += clock64() - w0;
+        if (DEV && g_prof_row && tid == 0) wait_cycles += clock64() - w0;
         const uint32_t sp = rg.slots + (uint32_t)(rg.c_slot * rg.SB) * 1024u + (uint32_t)lane * 16u;
-        if (P.flags & 64) {
+        if (DEV && (P.flags & 64)) {
           kbi += nb;  // (experiment: consume the ring without touching the data)
           if (kbi > KB) kbi -= KB;
         } else if (full) {
@@ -502,7 +506,7 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
               for (int n = 0; n < NT; ++n)
                 if (i < nb && n < nct) bq[i][n] = lds128(xb + (uint32_t)(i * 64 + n * 8 * xstride));
           }
-          if (!(P.flags & 16)) {  // (flag 16: experiment, skip the tensor work)
+          if (!(DEV && (P.flags & 16))) {  // (flag 16: experiment, skip the tensor work)
             if (PB == 4 && nb == 4) piece_full<NT, NACC, PB>(acc, sp, bq, nct);
             else piece_full<NT, NACC, 2>(acc, sp, bq, nct);
           }
@@ -534,7 +538,7 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
           kbi = 0;
           ++seg;
         }
-        ring_release(rg, P, lane, pol_stream, pol_keep);
+        ring_release<DEV>(rg, P, lane, pol_stream, pol_keep);
         if (!staged) {
 #pragma unroll
           for (int i = 0; i < PB; ++i)
@@ -544,7 +548,7 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
         u += nb;
       }
       if (kbi != 0) flush_acc<NT, NACC>(acc, pp + seg * (NT * 8) * PCOL, nct, t, g);
-      if (tid == 0 && g_prof_row) {  // warp 0: [5] cycles waiting for ring data; [7] run finished
+      if (DEV && tid == 0 && g_prof_row) {  // warp 0: [5] cycles waiting for ring data; [7] run finished
         g_prof_row[5] = (unsigned long long)wait_cycles;
         PROF_MARK(7);
       }
@@ -553,7 +557,7 @@ __device__ __forceinline__ uint32_t gemv_phase(const Phase& ph, const PMeta m, c
     PROF_MARK(3);
     // ---- cross-warp reduce + epilogue, one output element per thread-iteration
 #pragma unroll 1
-    for (int e = tid, it = 0; e < ((P.flags & 128) ? 0 : nelem); e += NTHREADS, ++it) {
+    for (int e = tid, it = 0; e < ((DEV && (P.flags & 128)) ? 0 : nelem); e += NTHREADS, ++it) {
       const int r = e & ((1 << rsh) - 1);
       const int tl = (e >> rsh) & ((1 << tbl) - 1);
       const int col = e >> (rsh + tbl);
