@@ -395,8 +395,16 @@ class Qwen3TTSTokenizer:
                         with_encoder=True, **kwargs) -> "Qwen3TTSTokenizer":
         """inference/qwen3_tts_tokenizer.py:63-99 — a local HF directory (config.json + safetensors of
         Qwen3TTSTokenizerV2Model).  `device_map` names the CUDA device; `dtype` / `attn_implementation` kwargs of the
-        reference are accepted and ignored (the engines fix their own precisions: bf16 tensor-core decoder, fp32 encoder)."""
+        reference are accepted; the engines fix their own precisions (bf16 tensor-core decoder, fp32 encoder) and a request
+        for an fp32 decoder is answered with a RuntimeWarning rather than silently narrowed."""
         from . import checkpoint
+        want = kwargs.get("dtype", kwargs.get("torch_dtype"))
+        if want is not None and str(want).replace("torch.", "") in ("float32", "float", "float64", "double"):
+            # not silent: the reference's standalone tokenizer (examples/test_tokenizer_12hz.py) runs in fp32
+            import warnings
+            warnings.warn(f"Qwen3TTSTokenizer: dtype={want} requested, but the B200 codec DECODER always computes in bf16 on the "
+                          "tensor cores (fp32 accumulation; ~30 dB SNR against an fp32 forward, DESIGN.md section 5); the "
+                          "ENCODER runs in fp32 and returns the same codes as the fp32 reference.", RuntimeWarning, stacklevel=2)
         d = checkpoint.resolve_dir(pretrained_model_name_or_path)
         cfg_json = checkpoint.read_json(os.path.join(d, "config.json"))
         mt = cfg_json.get("model_type", "qwen3_tts_tokenizer_12hz")

@@ -119,6 +119,13 @@ def test_from_pretrained_plumbing_with_stub_engines(tmp_path, monkeypatch):
     assert tok.get_decode_upsample_rate() == 1920 and tok.get_input_sample_rate() == 24000
     out = tok.encode(np.zeros(5000, np.float32), sr=24000)
     assert tuple(out.audio_codes[0].shape) == (3, 16)
+    # an fp32 decoder request is answered loudly (the decoder computes in bf16), a bf16 request is not
+    import warnings
+    with pytest.warns(RuntimeWarning, match="bf16"):
+        M.Qwen3TTSTokenizer.from_pretrained(str(tmp_path / "speech_tokenizer"), device_map="cpu", dtype=torch.float32)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error", RuntimeWarning)
+        M.Qwen3TTSTokenizer.from_pretrained(str(tmp_path / "speech_tokenizer"), device_map="cpu", dtype=torch.bfloat16)
     # a tokenizer directory of the wrong kind is refused
     import json
     json.dump({"model_type": "qwen3_tts_tokenizer_25hz"}, open(tmp_path / "speech_tokenizer" / "config.json", "w"))
