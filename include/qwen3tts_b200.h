@@ -196,6 +196,12 @@ void q3_codec_stream_close(q3_codec_stream* s);
 int q3_codec_total_upsample(q3_codec* c);
 /* kernels launched by the last q3_codec_forward (bench.py's gpu_launches bookkeeping) */
 int q3_codec_last_launch_count(q3_codec* c);
+/* Test hook (tests/ only): per-stage capture of the DECODER, so that an error in one small kernel cannot hide behind the
+ * waveform SNR.  The following q3_codec_forward calls copy the bf16 [B][T_stage][C_stage] tensor of `stage` into dst_dev
+ * (at most `capacity` elements): 0 pre_conv output (…v2.py:874), 1 pre-transformer output (:875-876), 2 output of the
+ * upsample stack (:878-880), 3 SnakeBeta(decoder.0 output) as fed to block 0 (:857,:646), 4+i output of decoder block i
+ * (:638-658).  stage < 0 clears all captures. */
+int q3_codec_debug_capture(q3_codec* c, int32_t stage, void* dst_dev, int64_t capacity);
 
 /* ---------------------------------------------------------------- codec ENCODER (Qwen3TTSTokenizer.encode)
  * Replaces Qwen3TTSTokenizerV2Model.encode (core/tokenizer_12hz/modeling_qwen3_tts_tokenizer_v2.py:961-991), i.e.

@@ -63,7 +63,7 @@ AR_SYMBOLS = ["q3_abi_version", "q3_last_error", "q3_engine_create", "q3_engine_
               "q3_algorithmic_bytes", "q3_set_profile", "q3_describe_frame_program", "q3_debug_time_phases", "q3_debug_set_skip",
               "q3_session_begin", "q3_admit", "q3_release_slots", "q3_append_trailing", "q3_set_hidden_capture"]
 CODEC_SYMBOLS = ["q3_codec_create", "q3_codec_destroy", "q3_codec_load_tensor", "q3_codec_finalize",
-                 "q3_codec_forward", "q3_codec_total_upsample", "q3_codec_last_launch_count",
+                 "q3_codec_forward", "q3_codec_total_upsample", "q3_codec_last_launch_count", "q3_codec_debug_capture",
                  "q3_codec_stream_open", "q3_codec_stream_step", "q3_codec_stream_reset", "q3_codec_stream_position", "q3_codec_stream_close",
                  "q3_codec_enc_create", "q3_codec_enc_destroy", "q3_codec_enc_load_tensor", "q3_codec_enc_finalize",
                  "q3_codec_enc_encode", "q3_codec_enc_frames", "q3_codec_enc_hop", "q3_codec_enc_last_launch_count",
@@ -134,6 +134,7 @@ def load():
         lib.q3_codec_stream_close.restype = None
         lib.q3_codec_total_upsample.argtypes = [vp]
         lib.q3_codec_last_launch_count.argtypes = [vp]
+        lib.q3_codec_debug_capture.argtypes = [vp, i32, vp, i64]
         lib.q3_codec_enc_create.argtypes = [C.POINTER(CodecEncCfg), C.POINTER(vp)]
         lib.q3_codec_enc_destroy.argtypes = [vp]
         lib.q3_codec_enc_destroy.restype = None

@@ -197,6 +197,38 @@ class CodecDecoder:
         self._keep = c
         return wav[:, None, :]
 
+    def stage_shapes(self, B: int, T: int):
+        """(name, (B, T_stage, C_stage)) of the stages q3_codec_debug_capture can copy, in stage-ordinal order."""
+        g = self.cfg
+        out = [("pre_conv", (B, T, g.latent_dim)), ("pre_transformer", (B, T, g.latent_dim))]
+        Tc = T
+        for f in g.upsampling_ratios:
+            Tc *= int(f)
+        out.append(("upsample", (B, Tc, g.latent_dim)))
+        C_ = g.decoder_dim
+        out.append(("decoder0_act", (B, Tc, C_)))
+        for i, r in enumerate(g.upsample_rates):
+            Tc *= int(r)
+            C_ //= 2
+            out.append((f"block{i}", (B, Tc, C_)))
+        return out
+
+    @torch.no_grad()
+    def forward_with_stages(self, codes: torch.Tensor):
+        """Test hook: forward() plus the bf16 channels-last tensor of every capturable stage (dict name -> (B,T,C))."""
+        B, K, T = codes.shape
+        bufs = {}
+        _lib.check(self.lib.q3_codec_debug_capture(self.h, -1, None, 0))
+        for i, (name, shp) in enumerate(self.stage_shapes(B, T)):
+            bufs[name] = torch.zeros(shp, dtype=torch.bfloat16, device=self.device)
+            _lib.check(self.lib.q3_codec_debug_capture(self.h, i, bufs[name].data_ptr(), bufs[name].numel()))
+        try:
+            wav = self.forward(codes)
+            torch.cuda.current_stream(self.device).synchronize()
+        finally:
+            _lib.check(self.lib.q3_codec_debug_capture(self.h, -1, None, 0))
+        return wav, bufs
+
     def open_stream(self, batch: int, max_packet_frames: int = 8) -> "CodecStream":
         """Stateful streaming decoder over `batch` rows (q3_codec_stream_*): push packets, get exactly the waveform of
         the full causal forward over everything pushed, for the cost of the new frames only."""

@@ -297,6 +297,8 @@ struct q3_codec {
   bool finalized = false;
   int total_up = 1;
   int launches = 0;
+  struct Capture { int stage; bf16* dst; int64_t capacity; };
+  std::vector<Capture> captures;  // test hook (q3_codec_debug_capture): stage ordinal -> destination of the next forward
 
   int alloc_bytes(void** p, size_t bytes) {
     cudaError_t e = cudaMalloc(p, bytes);
@@ -341,6 +343,18 @@ extern "C" void q3_codec_destroy(q3_codec* c) {
 
 extern "C" int q3_codec_total_upsample(q3_codec* c) { return c ? c->total_up : 0; }
 extern "C" int q3_codec_last_launch_count(q3_codec* c) { return c ? c->launches : 0; }
+
+// Test hook (tests/ only): the next q3_codec_forward calls copy the bf16 [B][T_stage][C_stage] tensor of `stage` into
+// dst_dev (at most `capacity` elements).  Stages: 0 pre_conv output, 1 pre-transformer output (after output_proj), 2 output
+// of the upsample stack, 3 SnakeBeta(decoder.0 conv output) as fed to block 0, 4+i output of decoder block i.
+// stage < 0 clears all captures.
+extern "C" int q3_codec_debug_capture(q3_codec* c, int32_t stage, void* dst_dev, int64_t capacity) {
+  Q3_REQUIRE(c, "null codec");
+  if (stage < 0) { c->captures.clear(); return 0; }
+  Q3_REQUIRE(dst_dev && capacity > 0, "bad capture destination");
+  c->captures.push_back({stage, reinterpret_cast<bf16*>(dst_dev), capacity});
+  return 0;
+}
 
 // Engine-native tensors (converted from the reference state_dict by the Python host):
 // shape[] / ndim describe the tensor; dtype is inferred from the name suffix: names ending in ".w" / "table" /
@@ -419,6 +433,16 @@ struct Runner {
     if (gemm_launch(plan, stream)) { err = 1; return; }
     c->launches++;
   }
+  // test hook: copy a stage's [B][T][C] bf16 tensor to every destination registered for `stage` (no launch, no sync)
+  void capture(int stage, const bf16* x, int64_t elems) {
+    if (err) return;
+    for (const auto& cp : c->captures)
+      if (cp.stage == stage) {
+        const int64_t n = elems < cp.capacity ? elems : cp.capacity;
+        if (cudaMemcpyAsync(cp.dst, x, (size_t)n * 2, cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+          err = q3_set_err("codec: capture of stage %d failed", stage);
+      }
+  }
   const float* f32(const std::string& n, int64_t cnt) {
     const DevTensor* d = c->get(n);
     if (!d || d->numel != cnt || d->dtype != 1) { if (!err) err = q3_set_err("codec: fp32 tensor %s missing/wrong size", n.c_str()); return nullptr; }
@@ -476,6 +500,7 @@ extern "C" int q3_codec_forward(q3_codec* c, const int32_t* codes_dev, int32_t B
   // ---- pre_conv k=3 (…v2.py:839-843,874)
   { const int sh[3] = {-2, -1, 0}; GemmEpilogue e = none; e.bias = R.f32("pre_conv.b", Cl); e.out_raw = X;
     R.gemm(Y, T, g.codebook_dim, "pre_conv.w", Cl, 3, sh, e); }
+  R.capture(0, X, (int64_t)B * T * Cl);
   // ---- pre_transformer (…v2.py:501-575)
   { GemmEpilogue e = none; e.bias = R.f32("tr.in.b", Hh); e.out_raw = Y; R.gemm(X, T, Cl, "tr.in.w", Hh, 1, &zero, e); }
   bf16* xres = Y;  // residual stream [B][T][Hh]
@@ -498,6 +523,7 @@ extern "C" int q3_codec_forward(q3_codec* c, const int32_t* codes_dev, int32_t B
   rmsnorm_rows_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(xres, R.b16("tr.norm", Hh), X, rows, Hh, g.rms_eps);
   c->launches++;
   { GemmEpilogue e = none; e.bias = R.f32("tr.out.b", Cl); e.out_raw = Z; R.gemm(X, T, Hh, "tr.out.w", Cl, 1, &zero, e); }
+  R.capture(1, Z, (int64_t)B * T * Cl);
   // ---- upsample: ConvT(k=s=f) + ConvNeXt (…v2.py:845-855,878-880)
   bf16* cur = Z;  // [B][Tc][Cl]
   int Tc = T;
@@ -520,6 +546,7 @@ extern "C" int q3_codec_forward(q3_codec* c, const int32_t* codes_dev, int32_t B
       R.gemm(W, Tc, 4 * Cl, (p + ".pw2.w").c_str(), Cl, 1, &zero, e); }
     cur = o;
   }
+  R.capture(2, cur, (int64_t)B * Tc * Cl);
   // ---- decoder.0: conv k7 latent -> decoder_dim; epilogue applies block 0's SnakeBeta (…v2.py:857,646)
   int C = g.decoder_dim;
   bf16* act = X;  // snake-activated input of the next conv
@@ -529,6 +556,7 @@ extern "C" int q3_codec_forward(q3_codec* c, const int32_t* codes_dev, int32_t B
     e.snake_ib = R.f32("dec.0.snake_ib", C); e.out_act = act;
     R.gemm(cur, Tc, Cl, "dec.in.w", C, 7, sh, e);
   }
+  R.capture(3, act, (int64_t)B * Tc * C);  // SnakeBeta(decoder.0 output) with block 0's leading activation
   // ---- decoder blocks (…v2.py:638-658, :619-635)
   bf16 *y = Y, *tmp = Z, *act2 = W;
   for (int bi = 0; bi < g.n_upsample_rates && !R.err; ++bi) {
@@ -565,6 +593,7 @@ extern "C" int q3_codec_forward(q3_codec* c, const int32_t* codes_dev, int32_t B
         std::swap(y, act2);  // y <- new residual stream
       }
     }
+    R.capture(4 + bi, y, (int64_t)B * Tc * C);  // the block's output (residual stream after its three units)
   }
   if (R.err) return 1;
   // ---- final conv + clamp
