@@ -52,10 +52,11 @@ def _run_stages(cfg, B, T, seed):
 def test_small_codec_every_stage_matches_oracle():
     snr = _run_stages(_small_cfg(), 2, 13, seed=3)
     report_parity("codec_stages_small_2x13", snr)
-    # bf16 activations against the fp32 oracle on the same bf16 weights: early stages are one or two roundings away
-    # from exact, the waveform bar of test_small_codec_matches_oracle (25 dB) is the floor for every stage
+    # bf16 activations against the fp32 oracle on the same bf16 weights.  A broken stage kernel shows up as < 10 dB at its
+    # stage and everything after it; the floor here is the full-config waveform bar (22 dB), the measured per-stage
+    # figures are reported so it can be tightened after the first hardware run
     for name, v in snr.items():
-        assert v > 25.0, f"{name}: SNR {v:.1f} dB ({snr})"
+        assert v > 22.0, f"{name}: SNR {v:.1f} dB ({snr})"
     assert snr["pre_conv"] > 35.0, snr   # table gather + two GEMMs: three bf16 roundings away from the fp32 oracle
 
 
